@@ -1,0 +1,957 @@
+// C-ABI implementation of include/fea_gpu.h: device context, kernel launches, NCCL halo
+// exchange and scalar all-reduces.  One context = one GPU = one rank.  No CPU fallback:
+// every numerical entry point launches the sm_100a kernels in element_kernels.cuh and
+// sparse_kernels.cuh or fails with an error code.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fea_gpu.h"
+#include "element_kernels.cuh"
+#include "fea_plan.hpp"
+#include "sparse_kernels.cuh"
+
+namespace fea {
+void plan_counts(const Plan &pl, int64_t out[16]);
+}
+
+using fea::PcgCtl;
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+extern "C" const char *fea_gpu_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t fea_gpu_launch_count(void) { return g_launches.load(); }
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return FEA_GPU_ERR_CUDA;                                                           \
+    }                                                                                    \
+  } while (0)
+#define NC(call)                                                                         \
+  do {                                                                                   \
+    ncclResult_t r_ = (call);                                                            \
+    if (r_ != ncclSuccess) {                                                             \
+      g_err = std::string(#call) + ": " + ncclGetErrorString(r_);                        \
+      return FEA_GPU_ERR_NCCL;                                                           \
+    }                                                                                    \
+  } while (0)
+#define LAUNCHED()                                                                       \
+  do {                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    CU(cudaGetLastError());                                                              \
+  } while (0)
+#define TRY(expr)                                                                        \
+  do {                                                                                   \
+    int rc_ = (expr);                                                                    \
+    if (rc_ != FEA_GPU_OK) return rc_;                                                   \
+  } while (0)
+
+enum { PH_ELEM = 0, PH_GATHER_K, PH_GATHER_R, PH_BC, PH_PCG, PH_SPMV, PH_HALO, PH_COUNT };
+constexpr int SPMV_EVENT_POOL = 128;
+constexpr int MAX_PARTIALS = 4096;
+constexpr size_t FLUSH_BYTES = 512ull << 20;
+
+struct fea_gpu_ctx {
+  fea::Plan plan;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  bool has_comm = false;
+  int model = 0, ng = 5;
+  double lambda = 0, mu = 0;
+  int n_own = 0, n_local = 0, n_elems = 0, ne_pad = 0;
+  int64_t nnzb = 0;
+  int spmv_lpr = 16;
+  int pcg_batch = 32;
+
+  double *X0 = nullptr, *x = nullptr;
+  int32_t *conn_soa = nullptr;
+  double *F_soa = nullptr, *S_soa = nullptr, *Ke = nullptr, *Re = nullptr;
+  int32_t *browptr = nullptr, *bcol = nullptr, *cptr = nullptr, *rptr = nullptr, *rsrc = nullptr, *diag = nullptr;
+  uint32_t *csrc = nullptr;
+  double *vals = nullptr, *vals_saved = nullptr;
+  double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr;
+  uint8_t *pflag = nullptr;
+  double *pval = nullptr;
+  int32_t *inc_dof = nullptr;
+  double *inc_val = nullptr;
+  int n_inc = 0;
+  bool any_presc_value = false;
+  int32_t *send_nodes = nullptr;
+  double *send_buf = nullptr;
+  double *partials = nullptr;
+  unsigned int *counters = nullptr;
+  PcgCtl *ctl = nullptr;
+  PcgCtl *ctl_host = nullptr;
+  double *scalar = nullptr;        // device scratch scalar
+  unsigned long long *bad = nullptr;
+  void *flush = nullptr;
+  double *export_buf = nullptr;    // lazily allocated [n_elems][ng][9]
+
+  cudaEvent_t ev_a[PH_COUNT], ev_b[PH_COUNT];
+  bool ev_set[PH_COUNT];
+  cudaEvent_t sp_a[SPMV_EVENT_POOL], sp_b[SPMV_EVENT_POOL];
+  int sp_used = 0;
+  int last_iters = 0;
+  cudaEvent_t tm_a, tm_b;
+  std::vector<int32_t> own_count;  // owned nodes per rank
+};
+
+template <class T>
+static int dev_alloc(T **p, size_t n) {
+  CU(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+  return FEA_GPU_OK;
+}
+template <class T>
+static int dev_upload(T **p, const std::vector<T> &v, cudaStream_t s) {
+  TRY(dev_alloc(p, v.size()));
+  if (!v.empty()) CU(cudaMemcpyAsync(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+  return FEA_GPU_OK;
+}
+
+// Tet10 shape-function derivatives and the Gauss tables, stated as in the reference
+// (fea_solver.c:32-54 and :1306-1361) so the constants are the same doubles.
+static void host_tables(int ng, fea::ElemTables &t) {
+  double gp[5][4];
+  if (ng == 4) {
+    const double a = 0.58541020, b = 0.13819660, w = (1 / 4.) / 6.;
+    const double tab[4][4] = {{w, a, b, b}, {w, b, a, b}, {w, b, b, a}, {w, b, b, b}};
+    std::memcpy(gp, tab, sizeof(tab));
+  } else {
+    const double wc = (-4 / 5.) / 6., w = (9 / 20.) / 6.;
+    const double tab[5][4] = {{wc, 1 / 4., 1 / 4., 1 / 4.}, {w, 1 / 2., 1 / 6., 1 / 6.},
+                              {w, 1 / 6., 1 / 2., 1 / 6.}, {w, 1 / 6., 1 / 6., 1 / 2.},
+                              {w, 1 / 6., 1 / 6., 1 / 6.}};
+    std::memcpy(gp, tab, sizeof(tab));
+  }
+  std::memset(&t, 0, sizeof(t));
+  for (int g = 0; g < ng; ++g) {
+    const double r = gp[g][1], s = gp[g][2], u = gp[g][3];
+    t.w[g] = gp[g][0];
+    const double d0 = 4 * u + 4 * s + 4 * r - 3;
+    const double dr[10] = {d0, 4 * r - 1, 0, 0, -4 * u - 4 * s - 8 * r + 4, 4 * s, -4 * s, -4 * u, 4 * u, 0};
+    const double ds[10] = {d0, 0, 4 * s - 1, 0, -4 * r, 4 * r, -4 * u - 8 * s - 4 * r + 4, -4 * u, 0, 4 * u};
+    const double dt[10] = {d0, 0, 0, 4 * u - 1, -4 * r, 0, -4 * s, -8 * u - 4 * s - 4 * r + 4, 4 * r, 4 * s};
+    for (int a = 0; a < 10; ++a) {
+      t.dN[g][0][a] = dr[a];
+      t.dN[g][1][a] = ds[a];
+      t.dN[g][2][a] = dt[a];
+    }
+  }
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+static void phase_begin(fea_gpu_ctx *c, int ph) { cudaEventRecord(c->ev_a[ph], c->stream); }
+static void phase_end(fea_gpu_ctx *c, int ph) {
+  cudaEventRecord(c->ev_b[ph], c->stream);
+  c->ev_set[ph] = true;
+}
+
+// ---------------------------------------------------------------------------------
+// halo exchange of a [n_local][3] vector: owners push their interface entries to the
+// ranks that hold them as ghosts.  Ghosts of one owner are contiguous, so
+// ncclRecv lands in place.
+
+static int halo_exchange(fea_gpu_ctx *c, double *vec) {
+  const fea::Plan &pl = c->plan;
+  if (!c->has_comm || pl.nbr_rank.empty()) return FEA_GPU_OK;
+  const int n_send = (int)pl.send_nodes.size();
+  if (n_send) {
+    fea::pack_kernel<<<cdiv(3 * (int64_t)n_send, 256), 256, 0, c->stream>>>(n_send, c->send_nodes, vec, c->send_buf);
+    LAUNCHED();
+  }
+  NC(ncclGroupStart());
+  for (size_t i = 0; i < pl.nbr_rank.size(); ++i) {
+    const int ns = pl.send_ptr[i + 1] - pl.send_ptr[i], nr = pl.recv_ptr[i + 1] - pl.recv_ptr[i];
+    if (ns) NC(ncclSend(c->send_buf + 3 * (size_t)pl.send_ptr[i], 3 * (size_t)ns, ncclDouble, pl.nbr_rank[i], c->comm, c->stream));
+    if (nr) NC(ncclRecv(vec + 3 * ((size_t)c->n_own + pl.recv_ptr[i]), 3 * (size_t)nr, ncclDouble, pl.nbr_rank[i], c->comm, c->stream));
+  }
+  NC(ncclGroupEnd());
+  return FEA_GPU_OK;
+}
+
+static int allreduce_sum(fea_gpu_ctx *c, double *dev, int count) {
+  if (!c->has_comm) return FEA_GPU_OK;
+  NC(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+
+extern "C" int fea_gpu_nccl_unique_id(void *out128) {
+  if (!out128) return FEA_GPU_ERR_ARG;
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(out128, &id, 128);
+  return FEA_GPU_OK;
+}
+
+static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const double *X0,
+                       const int32_t *conn, int32_t n_presc, const int32_t *presc_node,
+                       const int32_t *presc_type, const double *presc_vals, int rank, int nranks,
+                       const void *nccl_id) {
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0 || c->device >= ndev) {
+    g_err = "no CUDA device (this library has no CPU path)";
+    return FEA_GPU_ERR_CUDA;
+  }
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+  try {
+    fea::build_plan(c->plan, n_nodes, n_elems, X0, conn, rank, nranks);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return FEA_GPU_ERR_MESH;
+  }
+  const fea::Plan &pl = c->plan;
+  c->n_own = pl.n_own;
+  c->n_local = pl.n_local;
+  c->n_elems = pl.n_elems;
+  c->ne_pad = (pl.n_elems + 31) / 32 * 32;
+  c->nnzb = pl.nnzb();
+  if (const char *s = getenv("FEA_SPMV_LPR")) {
+    int v = atoi(s);
+    if (v == 4 || v == 8 || v == 16 || v == 32) c->spmv_lpr = v;
+  }
+  if (const char *s = getenv("FEA_PCG_BATCH")) {
+    int v = atoi(s);
+    if (v >= 1 && v <= 4096) c->pcg_batch = v;
+  }
+
+  if (nranks > 1) {
+    if (!nccl_id) {
+      g_err = "nranks > 1 needs a ncclUniqueId";
+      return FEA_GPU_ERR_ARG;
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_id, 128);
+    NC(ncclCommInitRank(&c->comm, nranks, id, rank));
+    c->has_comm = true;
+  }
+  c->own_count.assign((size_t)nranks, 0);
+  for (int32_t i = 0; i < n_nodes; ++i) c->own_count[(size_t)pl.owner[(size_t)i]]++;
+
+  // coordinates in local numbering
+  {
+    std::vector<double> xl(3 * (size_t)pl.n_local);
+    for (int32_t l = 0; l < pl.n_local; ++l)
+      for (int d = 0; d < 3; ++d) xl[3 * (size_t)l + d] = X0[3 * (size_t)pl.node_gid[(size_t)l] + d];
+    TRY(dev_upload(&c->X0, xl, c->stream));
+    TRY(dev_upload(&c->x, xl, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  {
+    std::vector<int32_t> soa(10 * (size_t)c->ne_pad, 0);
+    for (int32_t e = 0; e < pl.n_elems; ++e)
+      for (int a = 0; a < 10; ++a) soa[(size_t)a * c->ne_pad + e] = pl.conn[(size_t)e * 10 + a];
+    TRY(dev_upload(&c->conn_soa, soa, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  TRY(dev_upload(&c->browptr, pl.browptr, c->stream));
+  TRY(dev_upload(&c->bcol, pl.bcol, c->stream));
+  TRY(dev_upload(&c->cptr, pl.cptr, c->stream));
+  TRY(dev_upload(&c->csrc, pl.csrc, c->stream));
+  TRY(dev_upload(&c->rptr, pl.rptr, c->stream));
+  TRY(dev_upload(&c->rsrc, pl.rsrc, c->stream));
+  TRY(dev_upload(&c->diag, pl.diag, c->stream));
+  TRY(dev_upload(&c->send_nodes, pl.send_nodes, c->stream));
+  TRY(dev_alloc(&c->send_buf, 3 * pl.send_nodes.size()));
+
+  // prescribed DOFs: flags for owned+ghost DOFs, summed increments (the reference adds
+  // every list entry, fea_solver.c:1210-1240), last value for the RHS (:1256)
+  {
+    std::vector<int32_t> g2l((size_t)n_nodes, -1);
+    for (int32_t l = 0; l < pl.n_local; ++l) g2l[(size_t)pl.node_gid[(size_t)l]] = l;
+    std::vector<uint8_t> flag(3 * (size_t)pl.n_local, 0);
+    std::vector<double> val(3 * (size_t)pl.n_local, 0.0), inc(3 * (size_t)pl.n_local, 0.0);
+    for (int32_t k = 0; k < n_presc; ++k) {
+      if (presc_node[k] < 0 || presc_node[k] >= n_nodes) {
+        g_err = "prescribed node id out of range";
+        return FEA_GPU_ERR_MESH;
+      }
+      const int32_t l = g2l[(size_t)presc_node[k]];
+      if (l < 0) continue;
+      const int type = presc_type[k];
+      if (type < 0 || type > 7) continue;  // the reference matches only the 8 enum values
+      for (int d = 0; d < 3; ++d)
+        if (type & (1 << d)) {
+          flag[3 * (size_t)l + d] = 1;
+          val[3 * (size_t)l + d] = presc_vals[3 * (size_t)k + d];
+          inc[3 * (size_t)l + d] += presc_vals[3 * (size_t)k + d];
+          if (presc_vals[3 * (size_t)k + d] != 0.0) c->any_presc_value = true;
+        }
+    }
+    std::vector<int32_t> idof;
+    std::vector<double> ival;
+    for (size_t t = 0; t < flag.size(); ++t)
+      if (flag[t]) {
+        idof.push_back((int32_t)t);
+        ival.push_back(inc[t]);
+      }
+    c->n_inc = (int)idof.size();
+    TRY(dev_upload(&c->pflag, flag, c->stream));
+    TRY(dev_upload(&c->pval, val, c->stream));
+    TRY(dev_upload(&c->inc_dof, idof, c->stream));
+    TRY(dev_upload(&c->inc_val, ival, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+
+  const size_t n3 = 3 * (size_t)c->n_own, nl3 = 3 * (size_t)c->n_local;
+  TRY(dev_alloc(&c->F_soa, (size_t)c->ng * 9 * c->ne_pad));
+  TRY(dev_alloc(&c->S_soa, (size_t)c->ng * 9 * c->ne_pad));
+  TRY(dev_alloc(&c->Ke, (size_t)c->n_elems * 55 * 9));
+  TRY(dev_alloc(&c->Re, (size_t)30 * c->ne_pad));
+  TRY(dev_alloc(&c->vals, (size_t)c->nnzb * 9));
+  TRY(dev_alloc(&c->R, n3));
+  TRY(dev_alloc(&c->u, nl3));
+  TRY(dev_alloc(&c->p, nl3));
+  TRY(dev_alloc(&c->q, n3));
+  TRY(dev_alloc(&c->r, n3));
+  TRY(dev_alloc(&c->dinv, n3));
+  TRY(dev_alloc(&c->partials, 3 * (size_t)MAX_PARTIALS));
+  TRY(dev_alloc(&c->counters, 8));
+  TRY(dev_alloc(&c->ctl, 1));
+  TRY(dev_alloc(&c->scalar, 4));
+  TRY(dev_alloc(&c->bad, 1));
+  CU(cudaHostAlloc((void **)&c->ctl_host, sizeof(PcgCtl), cudaHostAllocDefault));
+  CU(cudaMemsetAsync(c->F_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
+  CU(cudaMemsetAsync(c->S_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
+  CU(cudaMemsetAsync(c->vals, 0, sizeof(double) * (size_t)c->nnzb * 9, c->stream));
+  CU(cudaMemsetAsync(c->R, 0, sizeof(double) * n3, c->stream));
+  CU(cudaMemsetAsync(c->u, 0, sizeof(double) * nl3, c->stream));
+  CU(cudaMemsetAsync(c->p, 0, sizeof(double) * nl3, c->stream));
+  CU(cudaMemsetAsync(c->counters, 0, sizeof(unsigned int) * 8, c->stream));
+  CU(cudaMemsetAsync(c->ctl, 0, sizeof(PcgCtl), c->stream));
+  CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
+
+  fea::ElemTables tab;
+  host_tables(c->ng, tab);
+  CU(cudaMemcpyToSymbolAsync(fea::c_tab, &tab, sizeof(tab), 0, cudaMemcpyHostToDevice, c->stream));
+
+  for (int i = 0; i < PH_COUNT; ++i) {
+    CU(cudaEventCreate(&c->ev_a[i]));
+    CU(cudaEventCreate(&c->ev_b[i]));
+    c->ev_set[i] = false;
+  }
+  for (int i = 0; i < SPMV_EVENT_POOL; ++i) {
+    CU(cudaEventCreate(&c->sp_a[i]));
+    CU(cudaEventCreate(&c->sp_b[i]));
+  }
+  CU(cudaEventCreate(&c->tm_a));
+  CU(cudaEventCreate(&c->tm_b));
+  CU(cudaStreamSynchronize(c->stream));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_create(fea_gpu_handle *out, int32_t n_nodes, int32_t n_elems, const double *X0,
+                              const int32_t *conn, int32_t model_type, double lambda, double mu,
+                              int32_t n_gauss, int32_t n_presc, const int32_t *presc_node,
+                              const int32_t *presc_type, const double *presc_vals, int32_t rank,
+                              int32_t nranks, const void *nccl_unique_id, int32_t device) {
+  if (!out || !X0 || !conn || n_nodes <= 0 || n_elems <= 0) {
+    g_err = "null or empty mesh";
+    return FEA_GPU_ERR_ARG;
+  }
+  if (model_type != FEA_MODEL_A5 && model_type != FEA_MODEL_COMPRESSIBLE_NEOHOOKEAN) {
+    g_err = "unknown model_type";
+    return FEA_GPU_ERR_ARG;
+  }
+  if (n_gauss != 4 && n_gauss != 5) {  // fea_solver.c:1495-1504
+    g_err = "gauss nodes count must be 4 or 5";
+    return FEA_GPU_ERR_ARG;
+  }
+  if (n_presc < 0 || (n_presc > 0 && (!presc_node || !presc_type || !presc_vals))) {
+    g_err = "bad prescribed-displacement arrays";
+    return FEA_GPU_ERR_ARG;
+  }
+  fea_gpu_ctx *c = new fea_gpu_ctx();
+  c->device = device;
+  c->model = model_type;
+  c->ng = n_gauss;
+  c->lambda = lambda;
+  c->mu = mu;
+  int rc = create_impl(c, n_nodes, n_elems, X0, conn, n_presc, presc_node, presc_type, presc_vals,
+                       rank, nranks, nccl_unique_id);
+  if (rc != FEA_GPU_OK) {
+    fea_gpu_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
+  if (!c) return FEA_GPU_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->has_comm) ncclCommDestroy(c->comm);
+  void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->browptr, c->bcol,
+                  c->cptr, c->rptr, c->rsrc, c->diag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
+                  c->p, c->q, c->r, c->dinv, c->pflag, c->pval, c->inc_dof, c->inc_val,
+                  c->send_nodes, c->send_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
+                  c->flush, c->export_buf};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (c->ctl_host) cudaFreeHost(c->ctl_host);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return FEA_GPU_OK;
+}
+
+#define CHECK_H(h)                                                                       \
+  do {                                                                                   \
+    if (!(h)) {                                                                          \
+      g_err = "null handle";                                                             \
+      return FEA_GPU_ERR_ARG;                                                            \
+    }                                                                                    \
+    CU(cudaSetDevice((h)->device));                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// vectors between the caller's global numbering and the rank-local device layout
+
+static int gather_owned(fea_gpu_ctx *c, const double *dev_vec, double *host_global) {
+  const fea::Plan &pl = c->plan;
+  if (!c->has_comm) {
+    std::vector<double> tmp(3 * (size_t)c->n_own);
+    CU(cudaMemcpyAsync(tmp.data(), dev_vec, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int32_t l = 0; l < c->n_own; ++l)
+      std::memcpy(host_global + 3 * (size_t)pl.node_gid[(size_t)l], tmp.data() + 3 * (size_t)l, 3 * sizeof(double));
+    return FEA_GPU_OK;
+  }
+  // all-gather of equally padded owned blocks, then placement by the shared owner map
+  int32_t maxown = 0;
+  for (int32_t v : c->own_count) maxown = std::max(maxown, v);
+  const size_t blk = 3 * (size_t)maxown;
+  double *sbuf = nullptr, *rbuf = nullptr;
+  TRY(dev_alloc(&sbuf, blk));
+  TRY(dev_alloc(&rbuf, blk * (size_t)pl.nranks));
+  CU(cudaMemsetAsync(sbuf, 0, sizeof(double) * blk, c->stream));
+  CU(cudaMemcpyAsync(sbuf, dev_vec, sizeof(double) * 3 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
+  NC(ncclAllGather(sbuf, rbuf, blk, ncclDouble, c->comm, c->stream));
+  std::vector<double> tmp(blk * (size_t)pl.nranks);
+  CU(cudaMemcpyAsync(tmp.data(), rbuf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<int32_t> pos((size_t)pl.nranks, 0);
+  for (int64_t g = 0; g < pl.n_nodes_global; ++g) {  // owned lists are ascending in global id
+    const int o = pl.owner[(size_t)g];
+    std::memcpy(host_global + 3 * (size_t)g, tmp.data() + blk * (size_t)o + 3 * (size_t)pos[(size_t)o]++, 3 * sizeof(double));
+  }
+  cudaFree(sbuf);
+  cudaFree(rbuf);
+  return FEA_GPU_OK;
+}
+
+static int scatter_local(fea_gpu_ctx *c, const double *host_global, double *dev_vec, int n_nodes_local) {
+  const fea::Plan &pl = c->plan;
+  std::vector<double> tmp(3 * (size_t)n_nodes_local);
+  for (int32_t l = 0; l < n_nodes_local; ++l)
+    std::memcpy(tmp.data() + 3 * (size_t)l, host_global + 3 * (size_t)pl.node_gid[(size_t)l], 3 * sizeof(double));
+  CU(cudaMemcpyAsync(dev_vec, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_set_nodes(fea_gpu_handle c, const double *x) {
+  CHECK_H(c);
+  if (!x) return FEA_GPU_ERR_ARG;
+  return scatter_local(c, x, c->x, c->n_local);
+}
+extern "C" int fea_gpu_get_nodes(fea_gpu_handle c, double *x) {
+  CHECK_H(c);
+  if (!x) return FEA_GPU_ERR_ARG;
+  return gather_owned(c, c->x, x);
+}
+extern "C" int fea_gpu_get_forces(fea_gpu_handle c, double *R) {
+  CHECK_H(c);
+  if (!R) return FEA_GPU_ERR_ARG;
+  return gather_owned(c, c->R, R);
+}
+extern "C" int fea_gpu_set_forces(fea_gpu_handle c, const double *R) {
+  CHECK_H(c);
+  if (!R) return FEA_GPU_ERR_ARG;
+  return scatter_local(c, R, c->R, c->n_own);
+}
+extern "C" int fea_gpu_get_solution(fea_gpu_handle c, double *u) {
+  CHECK_H(c);
+  if (!u) return FEA_GPU_ERR_ARG;
+  return gather_owned(c, c->u, u);
+}
+
+extern "C" int fea_gpu_apply_increment(fea_gpu_handle c, double lambda) {
+  CHECK_H(c);
+  if (c->n_inc) {
+    fea::increment_kernel<<<cdiv(c->n_inc, 256), 256, 0, c->stream>>>(c->n_inc, c->inc_dof, c->inc_val, lambda, c->x);
+    LAUNCHED();
+  }
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
+  CHECK_H(c);
+  const int n = 3 * c->n_own;
+  fea::axpy_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, 1.0, c->u, c->x);
+  LAUNCHED();
+  phase_begin(c, PH_HALO);
+  TRY(halo_exchange(c, c->x));
+  phase_end(c, PH_HALO);
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// element pass
+
+template <int MODEL, int NG>
+static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
+  const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
+  const size_t smem = sizeof(double) * NG * fea::NFIELD * 32;
+#define FEA_LAUNCH(K, Rr)                                                                          \
+  do {                                                                                             \
+    auto kern = fea::element_kernel<MODEL, NG, K, Rr>;                                             \
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    kern<<<grid, NG * 32, smem, c->stream>>>(args);                                                \
+  } while (0)
+  if (with_k && with_r) FEA_LAUNCH(true, true);
+  else if (with_k) FEA_LAUNCH(true, false);
+  else if (with_r) FEA_LAUNCH(false, true);
+  else FEA_LAUNCH(false, false);
+#undef FEA_LAUNCH
+  LAUNCHED();
+  return FEA_GPU_OK;
+}
+
+static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
+  fea::ElemArgs a;
+  a.n_elems = c->n_elems;
+  a.ne_pad = c->ne_pad;
+  a.conn_soa = c->conn_soa;
+  a.X0 = c->X0;
+  a.x = c->x;
+  a.lambda = c->lambda;
+  a.mu = c->mu;
+  a.F_soa = c->F_soa;
+  a.S_soa = c->S_soa;
+  a.Ke = c->Ke;
+  a.Re = c->Re;
+  a.bad = c->bad;
+  CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
+  phase_begin(c, PH_ELEM);
+  int rc;
+  if (c->model == FEA_MODEL_A5)
+    rc = c->ng == 5 ? launch_element<0, 5>(c, with_k, with_r, a) : launch_element<0, 4>(c, with_k, with_r, a);
+  else
+    rc = c->ng == 5 ? launch_element<1, 5>(c, with_k, with_r, a) : launch_element<1, 4>(c, with_k, with_r, a);
+  phase_end(c, PH_ELEM);
+  return rc;
+}
+
+static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
+  phase_begin(c, PH_GATHER_K);
+  const int grid = std::min(cdiv((int64_t)c->n_own * 32, 256), 148 * 16);
+  fea::gather_blocks_kernel<<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->cptr, c->csrc, c->Ke,
+                                                         c->vals, with_bc ? c->pflag : nullptr);
+  LAUNCHED();
+  phase_end(c, PH_GATHER_K);
+  return FEA_GPU_OK;
+}
+
+static int gather_residual(fea_gpu_ctx *c) {
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, nullptr);
+  LAUNCHED();
+  phase_end(c, PH_GATHER_R);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_update_state(fea_gpu_handle c) {
+  CHECK_H(c);
+  return element_pass(c, false, false);
+}
+extern "C" int fea_gpu_assemble_stiffness(fea_gpu_handle c) {
+  CHECK_H(c);
+  TRY(element_pass(c, true, false));
+  return gather_stiffness(c, false);
+}
+extern "C" int fea_gpu_assemble_residual(fea_gpu_handle c) {
+  CHECK_H(c);
+  TRY(element_pass(c, false, true));
+  return gather_residual(c);
+}
+extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t with_stiffness) {
+  CHECK_H(c);
+  TRY(element_pass(c, with_stiffness != 0, true));
+  if (with_stiffness) TRY(gather_stiffness(c, false));
+  return gather_residual(c);
+}
+
+extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
+  CHECK_H(c);
+  if (!count) return FEA_GPU_ERR_ARG;
+  unsigned long long v = 0;
+  CU(cudaMemcpyAsync(&v, c->bad, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *count = (int64_t)v;
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// SpMV / BC / PCG
+
+static int launch_spmv(fea_gpu_ctx *c, const double *x, double *y, bool fuse_dot) {
+  const int lpr = c->spmv_lpr;
+  const int grid = std::min(cdiv((int64_t)c->n_own * lpr, 256), MAX_PARTIALS);
+#define FEA_SPMV(L)                                                                                        \
+  do {                                                                                                     \
+    if (fuse_dot)                                                                                          \
+      fea::spmv_bsr_kernel<L, true><<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, x, y, \
+                                                                 c->partials, c->counters + 0, c->ctl);    \
+    else                                                                                                   \
+      fea::spmv_bsr_kernel<L, false><<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, x, y, \
+                                                                  c->partials, c->counters + 0, c->ctl);   \
+  } while (0)
+  switch (lpr) {
+    case 4: FEA_SPMV(4); break;
+    case 8: FEA_SPMV(8); break;
+    case 32: FEA_SPMV(32); break;
+    default: FEA_SPMV(16); break;
+  }
+#undef FEA_SPMV
+  LAUNCHED();
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
+  CHECK_H(c);
+  phase_begin(c, PH_BC);
+  const int n = 3 * c->n_own;
+  if (lambda != 0.0 && c->any_presc_value) {
+    // R -= K . (presc * lambda): the column sweep of solver_apply_single_bc (fea_solver.c:1250-1252)
+    CU(cudaMemsetAsync(c->p, 0, sizeof(double) * 3 * (size_t)c->n_local, c->stream));
+    fea::axpy_kernel<<<cdiv(3 * (int64_t)c->n_local, 256), 256, 0, c->stream>>>(3 * c->n_local, lambda, c->pval, c->p);
+    LAUNCHED();
+    TRY(launch_spmv(c, c->p, c->q, false));
+    fea::axpy_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, -1.0, c->q, c->R);
+    LAUNCHED();
+  }
+  const int grid = std::min(cdiv((int64_t)c->n_own * 32, 256), 148 * 16);
+  fea::cancel_kernel<<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, c->pflag);
+  LAUNCHED();
+  fea::rhs_fix_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->diag, c->pflag, c->pval, lambda, c->R);
+  LAUNCHED();
+  phase_end(c, PH_BC);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_save_stiffness(fea_gpu_handle c) {
+  CHECK_H(c);
+  if (!c->vals_saved) TRY(dev_alloc(&c->vals_saved, (size_t)c->nnzb * 9));
+  CU(cudaMemcpyAsync(c->vals_saved, c->vals, sizeof(double) * (size_t)c->nnzb * 9, cudaMemcpyDeviceToDevice, c->stream));
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_restore_stiffness(fea_gpu_handle c) {
+  CHECK_H(c);
+  if (!c->vals_saved) {
+    g_err = "no saved stiffness";
+    return FEA_GPU_ERR_ARG;
+  }
+  CU(cudaMemcpyAsync(c->vals, c->vals_saved, sizeof(double) * (size_t)c->nnzb * 9, cudaMemcpyDeviceToDevice, c->stream));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int32_t flags, int32_t *iters,
+                             double *relres) {
+  CHECK_H(c);
+  if (max_iter < 0 || !(tol >= 0.0)) return FEA_GPU_ERR_ARG;
+  const int n = 3 * c->n_own;
+  const bool multi = c->has_comm;
+  const int abs_tol = (flags & FEA_SOLVE_ABS_TOL) ? 1 : 0;
+  const int vgrid = std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS / 4);
+  phase_begin(c, PH_PCG);
+  c->sp_used = 0;
+
+  fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->diag, c->dinv);
+  LAUNCHED();
+  if (flags & FEA_SOLVE_X0_RHS) {
+    CU(cudaMemcpyAsync(c->u, c->R, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    TRY(halo_exchange(c, c->u));
+    TRY(launch_spmv(c, c->u, c->q, false));
+    fea::pcg_init_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->R, c->q, c->dinv, c->r, c->p, c->partials,
+                                                                    c->counters + 1, c->ctl, tol, abs_tol, !multi);
+  } else {
+    CU(cudaMemsetAsync(c->u, 0, sizeof(double) * (size_t)n, c->stream));
+    fea::pcg_init_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->R, nullptr, c->dinv, c->r, c->p,
+                                                                    c->partials, c->counters + 1, c->ctl, tol, abs_tol,
+                                                                    !multi);
+  }
+  LAUNCHED();
+  if (multi) {
+    TRY(allreduce_sum(c, &c->ctl->rz_new, 3));
+    fea::pcg_init_finalize_kernel<<<1, 1, 0, c->stream>>>(c->ctl, tol, abs_tol);
+    LAUNCHED();
+  }
+
+  int launched = 0;
+  bool done = false;
+  while (!done) {
+    const int batch = std::min(c->pcg_batch, max_iter - launched);
+    for (int b = 0; b < batch; ++b) {
+      TRY(halo_exchange(c, c->p));
+      const bool timed = c->sp_used < SPMV_EVENT_POOL;
+      if (timed) cudaEventRecord(c->sp_a[c->sp_used], c->stream);
+      TRY(launch_spmv(c, c->p, c->q, true));
+      if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);
+      if (multi) TRY(allreduce_sum(c, &c->ctl->pq, 1));
+      fea::pcg_update_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->p, c->q, c->dinv, c->u, c->r, c->partials,
+                                                                        c->counters + 2, c->ctl, !multi);
+      LAUNCHED();
+      if (multi) {
+        TRY(allreduce_sum(c, &c->ctl->rz_new, 2));
+        fea::pcg_control_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
+        LAUNCHED();
+      }
+      fea::pcg_direction_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, c->r, c->dinv, c->p, c->ctl);
+      LAUNCHED();
+    }
+    launched += batch;
+    CU(cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    done = c->ctl_host->done || launched >= max_iter;
+  }
+  phase_end(c, PH_PCG);
+  c->last_iters = c->ctl_host->iters;
+  if (iters) *iters = c->ctl_host->iters;
+  if (relres) *relres = c->ctl_host->bb > 0.0 ? std::sqrt(c->ctl_host->rr / c->ctl_host->bb) : 0.0;
+  if (!c->ctl_host->done) {
+    g_err = "PCG reached max_iter";
+    return FEA_GPU_ERR_NOT_CONVERGED;
+  }
+  if (!(c->ctl_host->rr == c->ctl_host->rr)) {
+    g_err = "PCG produced NaN";
+    return FEA_GPU_ERR_NOT_CONVERGED;
+  }
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_dot_R_u(fea_gpu_handle c, double *out) {
+  CHECK_H(c);
+  if (!out) return FEA_GPU_ERR_ARG;
+  const int n = 3 * c->n_own;
+  fea::dot_kernel<<<std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS), fea::RED_THREADS, 0, c->stream>>>(
+      n, c->R, c->u, c->partials, c->counters + 3, c->scalar);
+  LAUNCHED();
+  TRY(allreduce_sum(c, c->scalar, 1));
+  CU(cudaMemcpyAsync(out, c->scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_spmv(fea_gpu_handle c, const double *x, double *y) {
+  CHECK_H(c);
+  if (!x || !y) return FEA_GPU_ERR_ARG;
+  TRY(scatter_local(c, x, c->p, c->n_local));
+  TRY(launch_spmv(c, c->p, c->q, false));
+  return gather_owned(c, c->q, y);
+}
+
+extern "C" int fea_gpu_bench_spmv(fea_gpu_handle c, int32_t reps, double *ms_per_spmv) {
+  CHECK_H(c);
+  if (reps < 1 || !ms_per_spmv) return FEA_GPU_ERR_ARG;
+  TRY(launch_spmv(c, c->p, c->q, false));  // warm
+  CU(cudaEventRecord(c->tm_a, c->stream));
+  for (int i = 0; i < reps; ++i) TRY(launch_spmv(c, c->p, c->q, false));
+  CU(cudaEventRecord(c->tm_b, c->stream));
+  CU(cudaEventSynchronize(c->tm_b));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->tm_a, c->tm_b));
+  *ms_per_spmv = (double)ms / reps;
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// read-back
+
+extern "C" int fea_gpu_get_state(fea_gpu_handle c, double *graddefs, double *stresses) {
+  CHECK_H(c);
+  const fea::Plan &pl = c->plan;
+  const size_t per = (size_t)c->ng * 9;
+  if (!c->export_buf) TRY(dev_alloc(&c->export_buf, per * (size_t)c->n_elems));
+  std::vector<double> tmp(per * (size_t)c->n_elems);
+  for (int which = 0; which < 2; ++which) {
+    double *dst = which ? stresses : graddefs;
+    if (!dst) continue;
+    fea::state_export_kernel<<<cdiv((int64_t)per * c->n_elems, 256), 256, 0, c->stream>>>(
+        c->n_elems, c->ne_pad, c->ng, which ? c->S_soa : c->F_soa, c->export_buf);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(tmp.data(), c->export_buf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int32_t e = 0; e < c->n_elems; ++e)
+      if (pl.elem_owned[(size_t)e])
+        std::memcpy(dst + per * (size_t)pl.elem_gid[(size_t)e], tmp.data() + per * (size_t)e, sizeof(double) * per);
+  }
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, int32_t *rows, int32_t *rowptr,
+                               int32_t *colidx, double *vals) {
+  CHECK_H(c);
+  const fea::Plan &pl = c->plan;
+  if (n_rows) *n_rows = 3 * (int64_t)c->n_own;
+  if (nnz) *nnz = 9 * c->nnzb;
+  if (rows)
+    for (int32_t l = 0; l < c->n_own; ++l)
+      for (int i = 0; i < 3; ++i) rows[3 * (size_t)l + i] = 3 * pl.node_gid[(size_t)l] + i;
+  if (!rowptr && !colidx && !vals) return FEA_GPU_OK;
+  std::vector<double> bv;
+  if (vals) {
+    bv.resize(9 * (size_t)c->nnzb);
+    CU(cudaMemcpyAsync(bv.data(), c->vals, sizeof(double) * bv.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  // columns are ascending in LOCAL ids; re-sort each block row by GLOBAL id for the export
+  std::vector<std::pair<int32_t, int32_t>> order;
+  int64_t out = 0;
+  for (int32_t l = 0; l < c->n_own; ++l) {
+    const int32_t b0 = pl.browptr[(size_t)l], b1 = pl.browptr[(size_t)l + 1];
+    order.clear();
+    for (int32_t k = b0; k < b1; ++k) order.emplace_back(pl.node_gid[(size_t)pl.bcol[(size_t)k]], k);
+    std::sort(order.begin(), order.end());
+    for (int i = 0; i < 3; ++i) {
+      if (rowptr) rowptr[3 * (size_t)l + i] = (int32_t)out;
+      for (auto &pr : order)
+        for (int j = 0; j < 3; ++j, ++out) {
+          if (colidx) colidx[out] = 3 * pr.first + j;
+          if (vals) vals[out] = bv[9 * (size_t)pr.second + 3 * i + j];
+        }
+    }
+  }
+  if (rowptr) rowptr[3 * (size_t)c->n_own] = (int32_t)out;
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// introspection / measurement
+
+extern "C" int fea_gpu_counts(fea_gpu_handle c, int64_t out[16]) {
+  if (!c || !out) return FEA_GPU_ERR_ARG;
+  fea::plan_counts(c->plan, out);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_sync(fea_gpu_handle c) {
+  CHECK_H(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_timer_start(fea_gpu_handle c) {
+  CHECK_H(c);
+  CU(cudaEventRecord(c->tm_a, c->stream));
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_timer_stop(fea_gpu_handle c, double *ms) {
+  CHECK_H(c);
+  CU(cudaEventRecord(c->tm_b, c->stream));
+  CU(cudaEventSynchronize(c->tm_b));
+  float f = 0;
+  CU(cudaEventElapsedTime(&f, c->tm_a, c->tm_b));
+  if (ms) *ms = f;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
+  CHECK_H(c);
+  if (!out) return FEA_GPU_ERR_ARG;
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 16; ++i) out[i] = 0.0;
+  for (int i = 0; i < PH_COUNT; ++i) {
+    if (!c->ev_set[i] || i == PH_SPMV) continue;
+    float f = 0;
+    if (cudaEventElapsedTime(&f, c->ev_a[i], c->ev_b[i]) == cudaSuccess) out[i] = f;
+  }
+  double sp = 0;
+  for (int i = 0; i < c->sp_used; ++i) {
+    float f = 0;
+    if (cudaEventElapsedTime(&f, c->sp_a[i], c->sp_b[i]) == cudaSuccess) sp += f;
+  }
+  out[PH_SPMV] = c->sp_used ? sp / c->sp_used : 0.0;  // average ms per in-solve SpMV launch
+  out[8] = c->sp_used;
+  out[9] = c->last_iters;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_flush_l2(fea_gpu_handle c) {
+  CHECK_H(c);
+  if (!c->flush) CU(cudaMalloc(&c->flush, FLUSH_BYTES));
+  CU(cudaMemsetAsync(c->flush, 1, FLUSH_BYTES, c->stream));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs) {
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  float ms = 0;
+  if (dfma_tflops) {
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *out = nullptr;
+    CU(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CU(cudaEventRecord(a));
+      fea::dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+      g_launches.fetch_add(1);
+      CU(cudaEventRecord(b));
+      CU(cudaEventSynchronize(b));
+      CU(cudaEventElapsedTime(&ms, a, b));
+      const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    *dfma_tflops = best;
+    cudaFree(out);
+  }
+  if (copy_gbs) {
+    const size_t n = (size_t)1 << 26;  // 2 x 1 GiB
+    double2 *s = nullptr, *d = nullptr;
+    CU(cudaMalloc(&s, sizeof(double2) * n));
+    CU(cudaMalloc(&d, sizeof(double2) * n));
+    CU(cudaMemset(s, 0, sizeof(double2) * n));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+      CU(cudaEventRecord(a));
+      fea::copy_probe_kernel<<<prop.multiProcessorCount * 16, 512>>>(s, d, n);
+      g_launches.fetch_add(1);
+      CU(cudaEventRecord(b));
+      CU(cudaEventSynchronize(b));
+      CU(cudaEventElapsedTime(&ms, a, b));
+      const double gbs = 2.0 * sizeof(double2) * n / (ms * 1e-3) / 1e9;
+      if (rep > 0 && gbs > best) best = gbs;
+    }
+    *copy_gbs = best;
+    cudaFree(s);
+    cudaFree(d);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return FEA_GPU_OK;
+}

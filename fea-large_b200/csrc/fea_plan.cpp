@@ -1,0 +1,404 @@
+// Host-side planning for the B200 hot path (no CUDA in this file).
+//
+//  * partition: nodes are split into `nranks` contiguous chunks after sorting along the
+//    axis of largest extent (rows of K follow node ownership; an element is
+//    processed by every rank owning one of its nodes, so owned rows assemble locally).
+//  * symbolic phase: the sparsity pattern the reference obtains dynamically through
+//    sp_matrix_element_add (fea_solver.c:964-969, 1053-1058) -- a full 3x3 block for every
+//    node pair sharing an element, explicit zeros included -- is built up front as block
+//    CSR with ascending columns, together with the element->nonzero gather lists that make
+//    assembly atomic-free and order-deterministic (element-ascending, as the reference's
+//    element-major accumulation, fea_solver.c:878-882).
+#include "fea_plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+#include "../../include/fea_gpu.h"
+
+namespace fea {
+
+static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nranks) {
+  p.owner.assign((size_t)n_nodes, 0);
+  if (nranks <= 1) return;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int32_t i = 0; i < n_nodes; ++i)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], X0[3 * (size_t)i + d]);
+      hi[d] = std::max(hi[d], X0[3 * (size_t)i + d]);
+    }
+  int axis = 0;
+  for (int d = 1; d < 3; ++d)
+    if (hi[d] - lo[d] > hi[axis] - lo[axis]) axis = d;
+  std::vector<int32_t> order((size_t)n_nodes);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    double xa = X0[3 * (size_t)a + axis], xb = X0[3 * (size_t)b + axis];
+    return xa < xb || (xa == xb && a < b);
+  });
+  for (int64_t k = 0; k < n_nodes; ++k)
+    p.owner[(size_t)order[(size_t)k]] = (int32_t)(k * nranks / n_nodes);
+}
+
+void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
+                const int32_t *conn, int rank, int nranks) {
+  if (n_nodes <= 0 || n_elems <= 0 || !X0 || !conn) throw std::runtime_error("empty mesh");
+  if (rank < 0 || nranks < 1 || rank >= nranks) throw std::runtime_error("bad rank/nranks");
+  for (int64_t k = 0; k < (int64_t)n_elems * NEN; ++k)
+    if (conn[k] < 0 || conn[k] >= n_nodes) throw std::runtime_error("connectivity out of range");
+  p.rank = rank;
+  p.nranks = nranks;
+  p.n_nodes_global = n_nodes;
+  p.n_elems_global = n_elems;
+  partition_nodes(p, n_nodes, X0, nranks);
+  const std::vector<int32_t> &owner = p.owner;
+
+  // ---- local elements, local node numbering ---------------------------------
+  std::vector<uint8_t> used((size_t)n_nodes, 0);
+  p.elem_gid.clear();
+  for (int32_t e = 0; e < n_elems; ++e) {
+    const int32_t *c = conn + (size_t)e * NEN;
+    bool mine = false;
+    for (int a = 0; a < NEN; ++a) mine |= (owner[(size_t)c[a]] == rank);
+    if (!mine) continue;
+    p.elem_gid.push_back(e);
+    for (int a = 0; a < NEN; ++a) used[(size_t)c[a]] = 1;
+  }
+  p.n_elems = (int32_t)p.elem_gid.size();
+  if ((int64_t)p.n_elems * NTRI >= (int64_t)0x7fffffff)
+    throw std::runtime_error("too many local elements for 31-bit gather indices");
+
+  p.node_gid.clear();
+  for (int32_t i = 0; i < n_nodes; ++i)
+    if (owner[(size_t)i] == rank) p.node_gid.push_back(i);
+  p.n_own = (int32_t)p.node_gid.size();
+  {
+    std::vector<int32_t> ghosts;
+    for (int32_t i = 0; i < n_nodes; ++i)
+      if (used[(size_t)i] && owner[(size_t)i] != rank) ghosts.push_back(i);
+    std::sort(ghosts.begin(), ghosts.end(), [&](int32_t a, int32_t b) {
+      return owner[(size_t)a] < owner[(size_t)b] || (owner[(size_t)a] == owner[(size_t)b] && a < b);
+    });
+    p.node_gid.insert(p.node_gid.end(), ghosts.begin(), ghosts.end());
+  }
+  p.n_local = (int32_t)p.node_gid.size();
+  std::vector<int32_t> g2l((size_t)n_nodes, -1);
+  for (int32_t l = 0; l < p.n_local; ++l) g2l[(size_t)p.node_gid[(size_t)l]] = l;
+
+  p.conn.resize((size_t)p.n_elems * NEN);
+  p.elem_owned.resize((size_t)p.n_elems);
+  for (int32_t le = 0; le < p.n_elems; ++le) {
+    const int32_t *c = conn + (size_t)p.elem_gid[(size_t)le] * NEN;
+    for (int a = 0; a < NEN; ++a) p.conn[(size_t)le * NEN + a] = g2l[(size_t)c[a]];
+    p.elem_owned[(size_t)le] = owner[(size_t)c[0]] == rank;
+  }
+
+  // ---- node -> (element, local node) lists for owned nodes (residual gather) ---
+  const int32_t n_own = p.n_own;
+  p.rptr.assign((size_t)n_own + 1, 0);
+  for (int32_t le = 0; le < p.n_elems; ++le)
+    for (int a = 0; a < NEN; ++a) {
+      int32_t l = p.conn[(size_t)le * NEN + a];
+      if (l < n_own) p.rptr[(size_t)l + 1]++;
+    }
+  for (int32_t i = 0; i < n_own; ++i) p.rptr[(size_t)i + 1] += p.rptr[(size_t)i];
+  p.rsrc.resize((size_t)p.rptr[(size_t)n_own]);
+  {
+    std::vector<int32_t> cur(p.rptr.begin(), p.rptr.end() - 1);
+    for (int32_t le = 0; le < p.n_elems; ++le)      // ascending element order
+      for (int a = 0; a < NEN; ++a) {
+        int32_t l = p.conn[(size_t)le * NEN + a];
+        if (l < n_own) p.rsrc[(size_t)cur[(size_t)l]++] = le * NEN + a;
+      }
+  }
+
+  // ---- block pattern of the owned rows ---------------------------------------
+  p.browptr.assign((size_t)n_own + 1, 0);
+  std::vector<int32_t> rowlen((size_t)n_own, 0);
+#pragma omp parallel
+  {
+    std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 1024)
+    for (int32_t i = 0; i < n_own; ++i) {
+      tmp.clear();
+      tmp.push_back(i);
+      for (int32_t k = p.rptr[(size_t)i]; k < p.rptr[(size_t)i + 1]; ++k) {
+        const int32_t *c = &p.conn[(size_t)(p.rsrc[(size_t)k] / NEN) * NEN];
+        tmp.insert(tmp.end(), c, c + NEN);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      rowlen[(size_t)i] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    }
+  }
+  int64_t nnzb = 0;
+  for (int32_t i = 0; i < n_own; ++i) {
+    nnzb += rowlen[(size_t)i];
+    if (nnzb * 9 >= (int64_t)0x7fffffff) throw std::runtime_error("local matrix exceeds 2^31 scalar nonzeros");
+    p.browptr[(size_t)i + 1] = (int32_t)nnzb;
+  }
+  p.bcol.resize((size_t)nnzb);
+  p.diag.resize((size_t)n_own);
+  p.cptr.assign((size_t)nnzb + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 1024)
+    for (int32_t i = 0; i < n_own; ++i) {
+      tmp.clear();
+      tmp.push_back(i);
+      for (int32_t k = p.rptr[(size_t)i]; k < p.rptr[(size_t)i + 1]; ++k) {
+        const int32_t *c = &p.conn[(size_t)(p.rsrc[(size_t)k] / NEN) * NEN];
+        tmp.insert(tmp.end(), c, c + NEN);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      int32_t len = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+      int32_t *row = &p.bcol[(size_t)p.browptr[(size_t)i]];
+      std::copy(tmp.begin(), tmp.begin() + len, row);
+      p.diag[(size_t)i] = p.browptr[(size_t)i] + (int32_t)(std::lower_bound(row, row + len, i) - row);
+      // contribution counts (row-private range of cptr)
+      for (int32_t k = p.rptr[(size_t)i]; k < p.rptr[(size_t)i + 1]; ++k) {
+        const int32_t *c = &p.conn[(size_t)(p.rsrc[(size_t)k] / NEN) * NEN];
+        for (int b = 0; b < NEN; ++b) {
+          int32_t pos = p.browptr[(size_t)i] + (int32_t)(std::lower_bound(row, row + len, c[b]) - row);
+          p.cptr[(size_t)pos + 1]++;
+        }
+      }
+    }
+  }
+  for (int64_t k = 0; k < nnzb; ++k) {
+    int64_t s = (int64_t)p.cptr[(size_t)k] + p.cptr[(size_t)k + 1];
+    if (s >= (int64_t)0x7fffffff) throw std::runtime_error("gather map exceeds 2^31 entries");
+    p.cptr[(size_t)k + 1] = (int32_t)s;
+  }
+  p.csrc.resize((size_t)p.cptr[(size_t)nnzb]);
+#pragma omp parallel
+  {
+    std::vector<int32_t> cur;
+#pragma omp for schedule(dynamic, 1024)
+    for (int32_t i = 0; i < n_own; ++i) {
+      const int32_t r0 = p.browptr[(size_t)i], len = p.browptr[(size_t)i + 1] - r0;
+      const int32_t *row = &p.bcol[(size_t)r0];
+      cur.assign(p.cptr.begin() + r0, p.cptr.begin() + r0 + len);
+      for (int32_t k = p.rptr[(size_t)i]; k < p.rptr[(size_t)i + 1]; ++k) {   // element-ascending
+        const int32_t le = p.rsrc[(size_t)k] / NEN, a = p.rsrc[(size_t)k] % NEN;
+        const int32_t *c = &p.conn[(size_t)le * NEN];
+        for (int b = 0; b < NEN; ++b) {
+          int32_t pos = (int32_t)(std::lower_bound(row, row + len, c[b]) - row);
+          uint32_t src = (uint32_t)le * NTRI + (uint32_t)tri_index(std::min(a, b), std::max(a, b));
+          if (a > b) src |= SRC_TRANSPOSE;   // stored block is K_e[b][a]; K_e[a][b] is its transpose
+          p.csrc[(size_t)cur[(size_t)pos]++] = src;
+        }
+      }
+    }
+  }
+
+  // ---- halo lists ---------------------------------------------------------------
+  p.nbr_rank.clear();
+  p.send_ptr.assign(1, 0);
+  p.recv_ptr.assign(1, 0);
+  p.send_nodes.clear();
+  if (nranks > 1) {
+    std::vector<std::vector<int32_t>> send((size_t)nranks);
+    for (int32_t e = 0; e < n_elems; ++e) {
+      const int32_t *c = conn + (size_t)e * NEN;
+      int own[NEN];
+      bool has_me = false, has_other = false;
+      for (int a = 0; a < NEN; ++a) {
+        own[a] = owner[(size_t)c[a]];
+        has_me |= own[a] == rank;
+        has_other |= own[a] != rank;
+      }
+      if (!(has_me && has_other)) continue;
+      for (int a = 0; a < NEN; ++a) {
+        if (own[a] != rank) continue;
+        for (int b = 0; b < NEN; ++b)
+          if (own[b] != rank) send[(size_t)own[b]].push_back(c[a]);
+      }
+    }
+    int32_t ghost_pos = 0;
+    for (int q = 0; q < nranks; ++q) {
+      std::vector<int32_t> &s = send[(size_t)q];
+      std::sort(s.begin(), s.end());
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      int32_t nrecv = 0;
+      while (p.n_own + ghost_pos + nrecv < p.n_local &&
+             owner[(size_t)p.node_gid[(size_t)(p.n_own + ghost_pos + nrecv)]] == q)
+        ++nrecv;
+      if (s.empty() && nrecv == 0) continue;
+      p.nbr_rank.push_back(q);
+      for (int32_t g : s) p.send_nodes.push_back(g2l[(size_t)g]);
+      p.send_ptr.push_back((int32_t)p.send_nodes.size());
+      ghost_pos += nrecv;
+      p.recv_ptr.push_back(ghost_pos);
+    }
+  }
+}
+
+}  // namespace fea
+
+// ------------------------------------------------------------------------------
+// C-ABI: planning and mesh generation (host only)
+
+struct fea_plan {
+  fea::Plan plan;
+};
+
+static thread_local std::string g_plan_error;
+
+extern "C" int fea_plan_create(fea_plan_handle *out, int32_t n_nodes, int32_t n_elems,
+                               const double *X0, const int32_t *conn, int32_t rank,
+                               int32_t nranks) {
+  if (!out) return FEA_GPU_ERR_ARG;
+  fea_plan *p = new fea_plan();
+  try {
+    fea::build_plan(p->plan, n_nodes, n_elems, X0, conn, rank, nranks);
+  } catch (const std::exception &e) {
+    g_plan_error = e.what();
+    delete p;
+    return FEA_GPU_ERR_MESH;
+  }
+  *out = p;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_plan_destroy(fea_plan_handle p) {
+  delete p;
+  return FEA_GPU_OK;
+}
+
+namespace fea {
+void plan_counts(const Plan &pl, int64_t out[16]) {
+  std::memset(out, 0, sizeof(int64_t) * 16);
+  out[0] = pl.n_own;
+  out[1] = pl.n_local;
+  out[2] = pl.n_elems;
+  out[3] = pl.nnzb();
+  out[4] = (int64_t)pl.csrc.size();
+  out[5] = (int64_t)pl.nbr_rank.size();
+  out[6] = (int64_t)pl.send_nodes.size();
+  out[7] = pl.n_local - pl.n_own;
+  out[8] = pl.n_nodes_global;
+  out[9] = pl.n_elems_global;
+}
+}  // namespace fea
+
+extern "C" int fea_plan_counts(fea_plan_handle p, int64_t out[16]) {
+  if (!p || !out) return FEA_GPU_ERR_ARG;
+  fea::plan_counts(p->plan, out);
+  return FEA_GPU_OK;
+}
+
+template <class T, class U>
+static void copy_out(U *dst, const std::vector<T> &src) {
+  if (dst && !src.empty()) std::memcpy(dst, src.data(), sizeof(T) * src.size());
+}
+
+extern "C" int fea_plan_arrays(fea_plan_handle p, int32_t *local_node_gid,
+                               int32_t *local_elem_gid, int32_t *browptr, int32_t *bcol,
+                               int32_t *cptr, uint32_t *csrc, int32_t *nbr_rank,
+                               int32_t *send_ptr, int32_t *send_nodes, int32_t *recv_ptr) {
+  if (!p) return FEA_GPU_ERR_ARG;
+  const fea::Plan &pl = p->plan;
+  copy_out(local_node_gid, pl.node_gid);
+  copy_out(local_elem_gid, pl.elem_gid);
+  copy_out(browptr, pl.browptr);
+  copy_out(bcol, pl.bcol);
+  copy_out(cptr, pl.cptr);
+  copy_out(csrc, pl.csrc);
+  copy_out(nbr_rank, pl.nbr_rank);
+  copy_out(send_ptr, pl.send_ptr);
+  copy_out(send_nodes, pl.send_nodes);
+  copy_out(recv_ptr, pl.recv_ptr);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_plan_node_owner(fea_plan_handle p, int32_t *owner) {
+  if (!p || !owner) return FEA_GPU_ERR_ARG;
+  copy_out(owner, p->plan.owner);
+  return FEA_GPU_OK;
+}
+
+// Kuhn / Freudenthal subdivision: each cube is cut into the 6 tets that share the body
+// diagonal; all half-grid points become nodes (vertices + edge midpoints), so the node
+// count is exactly (2nx+1)(2ny+1)(2nz+1).  Local node order follows the
+// reference's shape functions (fea_solver.c:1287-1300): 0..3 vertices, 4=(0,1) 5=(1,2)
+// 6=(0,2) 7=(0,3) 8=(1,3) 9=(2,3); vertices are ordered for a positive Jacobian.
+extern "C" int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, double ly,
+                              double lz, double y0, int32_t bc_style, double dy,
+                              int64_t *n_nodes, int64_t *n_elems, int64_t *n_presc,
+                              double *nodes, int32_t *conn, int32_t *presc_node,
+                              int32_t *presc_type, double *presc_vals) {
+  if (nx < 1 || ny < 1 || nz < 1) return FEA_GPU_ERR_ARG;
+  const int64_t px = 2 * (int64_t)nx + 1, py = 2 * (int64_t)ny + 1, pz = 2 * (int64_t)nz + 1;
+  const int64_t nn = px * py * pz, ne = 6 * (int64_t)nx * ny * nz, np = 2 * px * pz;
+  if (nn >= 0x7fffffff || ne >= 0x7fffffff) return FEA_GPU_ERR_ARG;
+  if (n_nodes) *n_nodes = nn;
+  if (n_elems) *n_elems = ne;
+  if (n_presc) *n_presc = np;
+  auto nid = [&](int64_t jx, int64_t jy, int64_t jz) { return (int32_t)((jy * pz + jz) * px + jx); };
+  if (nodes) {
+#pragma omp parallel for schedule(static)
+    for (int64_t jy = 0; jy < py; ++jy)
+      for (int64_t jz = 0; jz < pz; ++jz)
+        for (int64_t jx = 0; jx < px; ++jx) {
+          double *x = nodes + 3 * (size_t)nid(jx, jy, jz);
+          x[0] = lx * (double)jx / (double)(px - 1);
+          x[1] = y0 + ly * (double)jy / (double)(py - 1);
+          x[2] = lz * (double)jz / (double)(pz - 1);
+        }
+  }
+  if (conn) {
+    // the 6 axis orders; odd permutations get vertices 2,3 ... handled by a sign test below
+    static const int perm[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    static const int edge[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+#pragma omp parallel for schedule(static)
+    for (int64_t cy = 0; cy < ny; ++cy)
+      for (int64_t cz = 0; cz < nz; ++cz)
+        for (int64_t cx = 0; cx < nx; ++cx) {
+          const int64_t cube = (cy * nz + cz) * nx + cx;
+          for (int t = 0; t < 6; ++t) {
+            int64_t v[4][3];
+            v[0][0] = 2 * cx; v[0][1] = 2 * cy; v[0][2] = 2 * cz;
+            for (int s = 0; s < 3; ++s) {
+              for (int d = 0; d < 3; ++d) v[s + 1][d] = v[s][d];
+              v[s + 1][perm[t][s]] += 2;
+            }
+            // orientation: det[v1-v0; v2-v0; v3-v0] > 0 (reference J = dN.x, :690-696)
+            int64_t a[3][3];
+            for (int r = 0; r < 3; ++r)
+              for (int d = 0; d < 3; ++d) a[r][d] = v[r + 1][d] - v[0][d];
+            int64_t det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
+                          a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                          a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+            if (det < 0)
+              for (int d = 0; d < 3; ++d) std::swap(v[1][d], v[2][d]);
+            int32_t *c = conn + (size_t)(cube * 6 + t) * 10;
+            for (int k = 0; k < 4; ++k) c[k] = nid(v[k][0], v[k][1], v[k][2]);
+            for (int k = 0; k < 6; ++k) {
+              const int64_t *p0 = v[edge[k][0]], *p1 = v[edge[k][1]];
+              c[4 + k] = nid((p0[0] + p1[0]) / 2, (p0[1] + p1[1]) / 2, (p0[2] + p1[2]) / 2);
+            }
+          }
+        }
+  }
+  if (presc_node && presc_type && presc_vals) {
+    int64_t k = 0;
+    for (int side = 0; side < 2; ++side) {
+      const int64_t jy = side ? py - 1 : 0;
+      for (int64_t jz = 0; jz < pz; ++jz)
+        for (int64_t jx = 0; jx < px; ++jx, ++k) {
+          presc_node[k] = nid(jx, jy, jz);
+          int type = bc_style == 1 ? 7 : 2;
+          if (bc_style == 0 && side == 0 && jx == 0 && jz == 0) type = 7;  // pin one corner
+          presc_type[k] = type;
+          presc_vals[3 * k + 0] = 0.0;
+          presc_vals[3 * k + 1] = side ? dy : 0.0;
+          presc_vals[3 * k + 2] = 0.0;
+        }
+    }
+  }
+  return FEA_GPU_OK;
+}

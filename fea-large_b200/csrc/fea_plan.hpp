@@ -1,0 +1,55 @@
+// Host-side plan: node-range partition, local numbering, block-CSR pattern and the
+// element -> nonzero gather map.  Pure C++ (no CUDA) so the N>1 logic is testable on a
+// CPU box.  Replaces what libspmatrix did implicitly in sp_matrix_element_add
+// (reference fea_solver.c:966,1055): the pattern is known before the first assembly.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace fea {
+
+constexpr int NEN = 10;                 // nodes per TETRAHEDRA10
+constexpr int NTRI = 55;                // upper-triangular (a<=b) node pairs per element
+constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
+
+// index of pair (a<=b) in the packed upper triangle, row-major
+inline int tri_index(int a, int b) { return a * NEN - (a * (a - 1)) / 2 + (b - a); }
+
+struct Plan {
+  int rank = 0, nranks = 1;
+  int64_t n_nodes_global = 0, n_elems_global = 0;
+
+  // local numbering: owned nodes (ascending global id) then ghosts (by owner, then id)
+  int32_t n_own = 0, n_local = 0, n_elems = 0;
+  std::vector<int32_t> node_gid;        // [n_local]
+  std::vector<int32_t> elem_gid;        // [n_elems] ascending
+  std::vector<int32_t> conn;            // [n_elems][10] local node ids
+  std::vector<uint8_t> elem_owned;      // [n_elems] 1 if this rank owns the element (owner of its node 0)
+  std::vector<int32_t> owner;           // [n_nodes_global]
+
+  // block CSR over owned rows
+  std::vector<int32_t> browptr;         // [n_own+1]
+  std::vector<int32_t> bcol;            // [nnzb] local node ids ascending
+  std::vector<int32_t> diag;            // [n_own] position of the diagonal block
+  // stiffness gather map
+  std::vector<int32_t> cptr;            // [nnzb+1]
+  std::vector<uint32_t> csrc;           // [ncontrib]
+  // residual gather map (node -> (element, local node))
+  std::vector<int32_t> rptr;            // [n_own+1]
+  std::vector<int32_t> rsrc;            // [.] elem*10 + a
+
+  // halo
+  std::vector<int32_t> nbr_rank;        // neighbour ranks ascending
+  std::vector<int32_t> send_ptr;        // [nbr+1]
+  std::vector<int32_t> send_nodes;      // local ids of owned nodes, per neighbour
+  std::vector<int32_t> recv_ptr;        // [nbr+1] offsets into the ghost range
+
+  int64_t nnzb() const { return (int64_t)bcol.size(); }
+};
+
+// throws std::runtime_error on bad meshes
+void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
+                const int32_t *conn, int rank, int nranks);
+
+}  // namespace fea

@@ -1,0 +1,380 @@
+// Sparse side of the hot path for sm_100a: deterministic gather assembly into 3x3-block
+// CSR, Dirichlet cancellation, block SpMV and the fused vector kernels of the
+// Jacobi-preconditioned CG.  All of this is HBM-bound streaming work: loads are
+// lane-contiguous over the value array, reductions are fixed-order (no floating-point
+// atomics), and the scalar recurrences of CG live on the device so a solve never waits
+// for the host between iterations.
+//
+// Replaces libspmatrix as used by the reference (fea_solver.c:179,194,251,304,877,966,
+// 1055,1255): sp_matrix_element_add -> gather_blocks_kernel, sp_matrix_cross_cancellation
+// -> cancel_kernel, sp_matrix_yale_solve_cg -> the pcg_* kernels.
+#pragma once
+#include <cstdint>
+
+namespace fea {
+
+constexpr int RED_THREADS = 256;
+
+// ---------------------------------------------------------------------------------
+// fixed-order block reduction of up to 2 values; result valid in thread 0
+
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem /* [NV][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    if (lane == 0) smem[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? smem[k * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      v[k] = t;
+    }
+  }
+}
+
+// Grid-wide deterministic sum: every block deposits its partial, the last block to
+// arrive adds the partials in index order.  Returns true in thread 0 of that last block
+// with the totals in v.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials /* [NV][grid] */,
+                                            unsigned int *counter, double *smem) {
+  __shared__ bool is_last;
+  block_reduce<NV>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = v[k];
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  double t[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    t[k] = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+      t[k] += ((volatile double *)partials)[(size_t)k * gridDim.x + i];
+  }
+  __syncthreads();
+  block_reduce<NV>(t, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = t[k];
+    *counter = 0u;
+  }
+  return threadIdx.x == 0;
+}
+
+// ---------------------------------------------------------------------------------
+// K3: gather assembly.  One warp per block row; lanes stride over the row's flat value
+// range so stores are contiguous.  Each scalar sums its contributions in the order of the
+// precomputed list (element-ascending), so results are bit-reproducible run to run.
+// Optionally applies the Dirichlet cancellation in the same pass.
+
+__global__ void __launch_bounds__(256)
+gather_blocks_kernel(int n_rows, const int32_t *__restrict__ browptr,
+                     const int32_t *__restrict__ bcol, const int32_t *__restrict__ cptr,
+                     const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
+                     double *__restrict__ vals, const uint8_t *__restrict__ pflag /* may be null */) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps_per_grid) {
+    const int f0 = browptr[row] * 9, f1 = browptr[row + 1] * 9;  // plan guarantees < 2^31
+    for (int f = f0 + lane; f < f1; f += 32) {
+      const int p = f / 9;
+      const int c = f - p * 9;
+      const int ct = (c % 3) * 3 + c / 3;
+      const int k0 = cptr[p], k1 = cptr[p + 1];
+      double acc = 0.0;
+      for (int k = k0; k < k1; ++k) {
+        const uint32_t s = csrc[k];
+        acc += Ke[(size_t)(s & 0x7fffffffu) * 9 + ((s >> 31) ? ct : c)];
+      }
+      if (pflag) {
+        const int i = c / 3, j = c - 3 * i;
+        const int colnode = bcol[p];
+        const bool diag = (colnode == row) && (i == j);
+        if (!diag && (pflag[3 * (size_t)row + i] | pflag[3 * (size_t)colnode + j])) acc = 0.0;
+      }
+      vals[f] = acc;
+    }
+  }
+}
+
+// residual gather: R[3I+i] = sum over (element, a) touching node I of R_e[a][i]
+__global__ void __launch_bounds__(256)
+gather_residual_kernel(int n_rows, const int32_t *__restrict__ rptr, const int32_t *__restrict__ rsrc,
+                       const double *__restrict__ Re, int ne_pad, double *__restrict__ R,
+                       const uint8_t *__restrict__ pflag /* may be null: zero prescribed rows */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n_rows) return;
+  const int row = t / 3, i = t - 3 * row;
+  double acc = 0.0;
+  for (int k = rptr[row]; k < rptr[row + 1]; ++k) {
+    const int s = rsrc[k];
+    const int e = s / 10, a = s - 10 * e;
+    acc += Re[(size_t)(a * 3 + i) * ne_pad + e];
+  }
+  if (pflag && pflag[t]) acc = 0.0;
+  R[t] = acc;
+}
+
+// K4: zero rows and columns of prescribed DOFs keeping the diagonal (sp_matrix_cross_cancellation
+// as used at fea_solver.c:1255); RHS rows become diag * presc (:1256)
+__global__ void __launch_bounds__(256)
+cancel_kernel(int n_rows, const int32_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
+              double *__restrict__ vals, const uint8_t *__restrict__ pflag) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps_per_grid) {
+    const int f0 = browptr[row] * 9, f1 = browptr[row + 1] * 9;
+    const uint8_t r0 = pflag[3 * (size_t)row], r1 = pflag[3 * (size_t)row + 1], r2 = pflag[3 * (size_t)row + 2];
+    for (int f = f0 + lane; f < f1; f += 32) {
+      const int p = f / 9;
+      const int c = f - p * 9;
+      const int i = c / 3, j = c - 3 * i;
+      const int colnode = bcol[p];
+      const uint8_t rf = i == 0 ? r0 : (i == 1 ? r1 : r2);
+      if ((rf | pflag[3 * (size_t)colnode + j]) && !((colnode == row) && (i == j))) vals[f] = 0.0;
+    }
+  }
+}
+
+__global__ void rhs_fix_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ diag,
+                               const uint8_t *__restrict__ pflag, const double *__restrict__ pval,
+                               double lambda, double *__restrict__ R) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (pflag[t]) {
+    const int row = t / 3, i = t - 3 * row;
+    R[t] = vals[(size_t)diag[row] * 9 + 4 * i] * (pval[t] * lambda);
+  }
+}
+
+__global__ void jacobi_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ diag,
+                              double *__restrict__ dinv) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int row = t / 3, i = t - 3 * row;
+  const double d = vals[(size_t)diag[row] * 9 + 4 * i];
+  dinv[t] = d != 0.0 ? 1.0 / d : 1.0;
+}
+
+// ---------------------------------------------------------------------------------
+// K5: y = A x for 3x3-block CSR.  LPR lanes cooperate on one block row; their loads walk
+// the row's value array contiguously (9 doubles per block, blocks back to back), x is
+// gathered through L1/L2.  Optionally fuses the partial of x_row . y_row (p.Ap of CG).
+
+struct PcgCtl {
+  double pq;        // p . A p (global)
+  double rz_old;    // r . z of the previous iteration
+  double rz_new;
+  double rr;        // r . r
+  double bb;        // b . b
+  double thresh;    // stop when rr <= thresh
+  double beta;
+  int done;
+  int iters;
+};
+
+template <int LPR, bool FUSE_DOT>
+__global__ void __launch_bounds__(256)
+spmv_bsr_kernel(int n_rows, const int32_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
+                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                double *partials, unsigned int *counter, PcgCtl *ctl) {
+  __shared__ double red[32];
+  if (FUSE_DOT && ctl->done) return;
+  const int sub = threadIdx.x % LPR;
+  constexpr int GROUPS = 256 / LPR;  // block rows handled per CTA per sweep
+  double dot = 0.0;
+  // the sweep bound depends on blockIdx only, so every lane of a warp reaches the shuffles
+  for (int base = blockIdx.x * GROUPS; base < n_rows; base += gridDim.x * GROUPS) {
+    const int row = base + threadIdx.x / LPR;
+    const bool valid = row < n_rows;
+    const int b0 = valid ? browptr[row] : 0, b1 = valid ? browptr[row + 1] : 0;
+    const int64_t f0 = (int64_t)b0 * 9;
+    const int nf = (b1 - b0) * 9;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int f = sub; f < nf; f += LPR) {
+      const int blk = f / 9;
+      const int c = f - blk * 9;
+      const int i = c / 3, j = c - 3 * i;
+      const double v = vals[f0 + f] * x[3 * (size_t)bcol[b0 + blk] + j];
+      a0 += (i == 0) ? v : 0.0;
+      a1 += (i == 1) ? v : 0.0;
+      a2 += (i == 2) ? v : 0.0;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      a0 += __shfl_down_sync(0xffffffffu, a0, o, LPR);
+      a1 += __shfl_down_sync(0xffffffffu, a1, o, LPR);
+      a2 += __shfl_down_sync(0xffffffffu, a2, o, LPR);
+    }
+    if (valid && sub == 0) {
+      y[3 * (size_t)row] = a0;
+      y[3 * (size_t)row + 1] = a1;
+      y[3 * (size_t)row + 2] = a2;
+      if (FUSE_DOT)
+        dot += a0 * x[3 * (size_t)row] + a1 * x[3 * (size_t)row + 1] + a2 * x[3 * (size_t)row + 2];
+    }
+  }
+  if (FUSE_DOT) {
+    double v[1] = {dot};
+    if (grid_reduce<1>(v, partials, counter, red)) ctl->pq = v[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// PCG vector kernels
+
+// r = b - q (q = A x0) or r = b; z = dinv r; p = z; sums r.z, b.b, r.r
+__global__ void __launch_bounds__(RED_THREADS)
+pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ q /* null: x0 = 0 */,
+                const double *__restrict__ dinv, double *__restrict__ r, double *__restrict__ p,
+                double *partials, unsigned int *counter, PcgCtl *ctl, double tol, int abs_tol, int finalize) {
+  __shared__ double red[3 * 32];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double bt = b[t];
+    const double rt = q ? bt - q[t] : bt;
+    const double zt = dinv[t] * rt;
+    r[t] = rt;
+    p[t] = zt;
+    s[0] += rt * zt;
+    s[1] += bt * bt;
+    s[2] += rt * rt;
+  }
+  if (grid_reduce<3>(s, partials, counter, red)) {
+    ctl->rz_old = s[0];
+    ctl->rz_new = s[0];
+    ctl->bb = s[1];
+    ctl->rr = s[2];
+    ctl->iters = 0;
+    ctl->beta = 0.0;
+    if (finalize) {
+      ctl->thresh = abs_tol ? tol * tol : tol * tol * s[1];
+      ctl->done = (s[1] == 0.0 || s[2] <= ctl->thresh) ? 1 : 0;
+    }
+  }
+}
+
+// multi-rank: fold the all-reduced sums of pcg_init into the control block
+__global__ void pcg_init_finalize_kernel(PcgCtl *ctl, double tol, int abs_tol) {
+  ctl->rz_old = ctl->rz_new;
+  ctl->thresh = abs_tol ? tol * tol : tol * tol * ctl->bb;
+  ctl->done = (ctl->bb == 0.0 || ctl->rr <= ctl->thresh) ? 1 : 0;
+}
+
+__device__ __forceinline__ void pcg_step_control(PcgCtl *ctl) {
+  ctl->beta = ctl->rz_new / ctl->rz_old;
+  ctl->rz_old = ctl->rz_new;
+  ctl->iters += 1;
+  if (ctl->rr <= ctl->thresh || !(ctl->rr == ctl->rr)) ctl->done = 1;
+}
+
+// u += alpha p; r -= alpha q; sums r.(dinv r), r.r.  With `finalize` (single rank) the last
+// block also advances the scalar recurrences.
+__global__ void __launch_bounds__(RED_THREADS)
+pcg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__ q,
+                  const double *__restrict__ dinv, double *__restrict__ u, double *__restrict__ r,
+                  double *partials, unsigned int *counter, PcgCtl *ctl, int finalize) {
+  __shared__ double red[2 * 32];
+  if (ctl->done) return;
+  const double alpha = ctl->rz_old / ctl->pq;
+  double s[2] = {0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    u[t] = fma(alpha, p[t], u[t]);
+    const double rt = fma(-alpha, q[t], r[t]);
+    r[t] = rt;
+    s[0] += rt * rt * dinv[t];
+    s[1] += rt * rt;
+  }
+  if (grid_reduce<2>(s, partials, counter, red)) {
+    ctl->rz_new = s[0];
+    ctl->rr = s[1];
+    if (finalize) pcg_step_control(ctl);
+  }
+}
+
+__global__ void pcg_control_kernel(PcgCtl *ctl) {
+  if (!ctl->done) pcg_step_control(ctl);
+}
+
+// p = dinv r + beta p
+__global__ void __launch_bounds__(256)
+pcg_direction_kernel(int n, const double *__restrict__ r, const double *__restrict__ dinv,
+                     double *__restrict__ p, const PcgCtl *ctl) {
+  if (ctl->done) return;
+  const double beta = ctl->beta;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    p[t] = fma(beta, p[t], dinv[t] * r[t]);
+}
+
+// out = a . b (fixed order)
+__global__ void __launch_bounds__(RED_THREADS)
+dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b, double *partials,
+           unsigned int *counter, double *out) {
+  __shared__ double red[32];
+  double s[1] = {0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) s[0] += a[t] * b[t];
+  if (grid_reduce<1>(s, partials, counter, red)) *out = s[0];
+}
+
+// ---------------------------------------------------------------------------------
+// small vector utilities
+
+__global__ void axpy_kernel(int n, double alpha, const double *__restrict__ x, double *__restrict__ y) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    y[t] = fma(alpha, x[t], y[t]);
+}
+
+// x[dof] += lambda * value for the (pre-aggregated) prescribed DOFs (fea_solver.c:1259-1266)
+__global__ void increment_kernel(int n, const int32_t *__restrict__ dof, const double *__restrict__ val,
+                                 double lambda, double *__restrict__ x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) x[dof[t]] += val[t] * lambda;
+}
+
+__global__ void pack_kernel(int n_nodes, const int32_t *__restrict__ nodes, const double *__restrict__ v,
+                            double *__restrict__ buf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * n_nodes) buf[t] = v[3 * (size_t)nodes[t / 3] + t % 3];
+}
+
+// [ng*9][ne_pad] -> [n_elems][ng][9] for elements flagged in `take`, scattered to global ids
+__global__ void state_export_kernel(int n_elems, int ne_pad, int ng, const double *__restrict__ soa,
+                                    double *__restrict__ aos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)ng * 9;
+  if (t >= (int64_t)n_elems * per) return;
+  const int e = (int)(t / per), f = (int)(t - (int64_t)e * per);
+  aos[t] = soa[(size_t)f * ne_pad + e];
+}
+
+// peak probes -------------------------------------------------------------------
+__global__ void dfma_probe_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void copy_probe_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+    dst[t] = src[t];
+}
+
+}  // namespace fea

@@ -1,0 +1,194 @@
+/*
+ * fea_gpu.h -- C-ABI of the B200 (sm_100a) finite-strain hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int return codes
+ * (0 = ok), no C++/torch types.  Each entry point names the reference
+ * function(s) of zbw2577/fea-large `solver-large/` it replaces.  The host C
+ * layer under fea-large_b200/host/ keeps the reference's own public names
+ * (solve(), solver_create_stiffness(), ...) and forwards to these.
+ *
+ * There is NO CPU fallback behind any of these calls: without a CUDA device
+ * fea_gpu_create() fails with FEA_GPU_ERR_CUDA.
+ *
+ * Numbering: `nodes`/`conn`/prescribed node ids are the caller's GLOBAL
+ * 0-based ids (sexp_loader.c:232, exporter.py:480).  With nranks > 1 every
+ * rank passes the same global mesh; the library partitions node ranges
+ * (matrix rows) and elements itself and talks NCCL.
+ */
+#ifndef FEA_GPU_H
+#define FEA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fea_gpu_ctx *fea_gpu_handle;
+typedef struct fea_plan *fea_plan_handle;
+
+enum {
+  FEA_GPU_OK = 0,
+  FEA_GPU_ERR_ARG = 1,      /* bad argument (null, size, unknown enum)       */
+  FEA_GPU_ERR_CUDA = 2,     /* CUDA runtime failure / no device              */
+  FEA_GPU_ERR_NCCL = 3,     /* NCCL failure                                  */
+  FEA_GPU_ERR_MESH = 4,     /* connectivity out of range, no elements, ...   */
+  FEA_GPU_ERR_NOT_CONVERGED = 5 /* fea_gpu_solve hit max_iter (u is still set) */
+};
+
+/* model_type, reference fea_model.h:37-40 */
+enum { FEA_MODEL_A5 = 0, FEA_MODEL_COMPRESSIBLE_NEOHOOKEAN = 1 };
+
+/* fea_gpu_solve() flags */
+enum {
+  FEA_SOLVE_X0_ZERO = 0,      /* start from u = 0                                        */
+  FEA_SOLVE_X0_RHS = 1,       /* start from u = R, as the reference call site does
+                                 (fea_solver.c:251-256 passes x0 = b)                    */
+  FEA_SOLVE_ABS_TOL = 2       /* stop on ||r||_2 <= tol instead of ||r||_2 <= tol*||b||_2 */
+};
+
+/* ---- lifetime --------------------------------------------------------- */
+
+/*
+ * Replaces fea_solver_alloc (fea_solver.c:387-456) + solver_create_element_database
+ * (:556) + fea_model_init (fea_model.c:7): uploads the mesh, builds the sparsity
+ * pattern (full 3x3 blocks for every node pair sharing an element, explicit
+ * zeros kept, columns ascending -- SURVEY 8c) and the element->nonzero gather map.
+ *
+ *   X0          [n_nodes][3] reference coordinates (nodes0_p); current = X0 at start (:400)
+ *   conn        [n_elems][10] TETRAHEDRA10 connectivity, reference node order (:1287-1300)
+ *   n_gauss     4 or 5 (gauss_nodes4/5_tetr10, :32-54)
+ *   presc_node/type/vals  prescribed_bnd_node array (fea_solver.h:142-157); type is the
+ *               presc_boundary_type bitmask 1=x 2=y 4=z (:74-83), vals [n_presc][3]
+ *   rank,nranks,nccl_unique_id  nranks==1 -> id may be NULL.  Otherwise 128 bytes of a
+ *               ncclUniqueId created by rank 0 and distributed by the caller.
+ *   device      CUDA device ordinal
+ */
+int fea_gpu_create(fea_gpu_handle *out, int32_t n_nodes, int32_t n_elems,
+                   const double *X0, const int32_t *conn, int32_t model_type,
+                   double lambda, double mu, int32_t n_gauss, int32_t n_presc,
+                   const int32_t *presc_node, const int32_t *presc_type,
+                   const double *presc_vals, int32_t rank, int32_t nranks,
+                   const void *nccl_unique_id, int32_t device);
+/* fea_solver_free (fea_solver.c:459-501) */
+int fea_gpu_destroy(fea_gpu_handle h);
+/* ncclGetUniqueId for the caller to broadcast (128 bytes) */
+int fea_gpu_nccl_unique_id(void *out128);
+const char *fea_gpu_last_error(void);
+
+/* ---- node coordinates -------------------------------------------------- */
+
+/* nodes_p <- x  (host [n_nodes][3], global ids); each rank takes its owned+ghost part */
+int fea_gpu_set_nodes(fea_gpu_handle h, const double *x);
+/* x <- nodes_p; with nranks>1 a collective (all-gather), every rank gets all nodes */
+int fea_gpu_get_nodes(fea_gpu_handle h, double *x);
+/* solver_update_nodes_with_bc(self, lambda) (fea_solver.c:1281, :1205-1242, :1259) */
+int fea_gpu_apply_increment(fea_gpu_handle h, double lambda);
+/* solver_update_nodes_with_solution(self, global_solution_vct) (:1270-1279) */
+int fea_gpu_update_nodes(fea_gpu_handle h);
+
+/* ---- element phase ----------------------------------------------------- */
+
+/* solver_create_current_shape_gradients (:831) + solver_create_stresses (:843):
+ * J, detJ, grad N, F (through F^-1, the CURRENT_SHAPE_GRADIENTS branch :1131-1152),
+ * Cauchy stress (fea_model.c:26/79) for every (element, Gauss point) */
+int fea_gpu_update_state(fea_gpu_handle h);
+/* solver_create_stiffness (:873): K_e constitutive (:887) + initial stress (:986),
+ * deterministic gather into the global matrix (replaces sp_matrix_element_add :966,:1055) */
+int fea_gpu_assemble_stiffness(fea_gpu_handle h);
+/* solver_create_residual_forces (:863, :1072-1114): global_forces_vct = -int sigma grad N */
+int fea_gpu_assemble_residual(fea_gpu_handle h);
+/* state + stiffness + residual from the current nodes in ONE element pass */
+int fea_gpu_assemble_all(fea_gpu_handle h, int32_t with_stiffness);
+/* solver_apply_prescribed_bc(self, lambda) (:1200, :1244-1257 + sp_matrix_cross_cancellation) */
+int fea_gpu_apply_bc(fea_gpu_handle h, double lambda);
+/* keep / restore the assembled matrix: sp_matrix_copy at :179 and :194-195 (modified Newton) */
+int fea_gpu_save_stiffness(fea_gpu_handle h);
+int fea_gpu_restore_stiffness(fea_gpu_handle h);
+
+/* ---- linear solve and Newton bookkeeping ------------------------------- */
+
+/* solver_solve_slae (:300-321): Jacobi-preconditioned CG on K u = R.
+ * iters/relres may be NULL.  Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter. */
+int fea_gpu_solve(fea_gpu_handle h, double tol, int32_t max_iter, int32_t flags,
+                  int32_t *iters, double *relres);
+/* cdot(global_forces_vct, global_solution_vct, n) at :208 */
+int fea_gpu_dot_R_u(fea_gpu_handle h, double *out);
+/* y = K x with host vectors in global numbering (tests / diagnostics) */
+int fea_gpu_spmv(fea_gpu_handle h, const double *x, double *y);
+
+/* ---- read-back (host arrays, global numbering) ------------------------- */
+
+/* graddefs / stresses [n_elems][n_gauss][3][3] (fea_solver.h:262-269).  With
+ * nranks>1 only elements owned by this rank are written. */
+int fea_gpu_get_state(fea_gpu_handle h, double *graddefs, double *stresses);
+int fea_gpu_get_forces(fea_gpu_handle h, double *R);      /* global_forces_vct   */
+int fea_gpu_set_forces(fea_gpu_handle h, const double *R);
+int fea_gpu_get_solution(fea_gpu_handle h, double *u);    /* global_solution_vct */
+/* scalar CSR of the rows this rank owns: int32 indices, columns ascending, explicit
+ * zeros kept.  Call with NULL arrays to get sizes: n_rows, nnz.  `rows` (may be NULL)
+ * receives the global DOF id of each returned row. */
+int fea_gpu_get_csr(fea_gpu_handle h, int64_t *n_rows, int64_t *nnz, int32_t *rows,
+                    int32_t *rowptr, int32_t *colidx, double *vals);
+/* elements whose |J| or det F was <= 0 (or J singular) in the last element pass */
+int fea_gpu_bad_points(fea_gpu_handle h, int64_t *count);
+
+/* ---- introspection / measurement --------------------------------------- */
+
+/* out[0]=owned nodes, [1]=local nodes (owned+ghost), [2]=local elements,
+ * [3]=block nonzeros (3x3), [4]=gather contributions, [5]=neighbour ranks,
+ * [6]=halo nodes sent, [7]=halo nodes received, [8]=global nodes, [9]=global elements */
+int fea_gpu_counts(fea_gpu_handle h, int64_t out[16]);
+/* kernels launched by this library in this process (all handles) */
+int64_t fea_gpu_launch_count(void);
+/* device-side stopwatch on the library's stream (CUDA events) */
+int fea_gpu_timer_start(fea_gpu_handle h);
+int fea_gpu_timer_stop(fea_gpu_handle h, double *ms);
+int fea_gpu_sync(fea_gpu_handle h);
+/* per-phase device time of the most recent call of each phase, ms:
+ * [0]=element kernel, [1]=matrix gather, [2]=residual gather, [3]=bc,
+ * [4]=pcg total, [5]=spmv (sum over iterations of the last solve), [6]=halo */
+int fea_gpu_phase_ms(fea_gpu_handle h, double out[16]);
+/* repeated SpMV on device vectors for roofline measurement: average ms per SpMV */
+int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);
+/* measured machine peaks on this device: FP64 FMA TFLOP/s, copy GB/s (read+write) */
+int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs);
+/* overwrite >= `bytes` of scratch so L2 holds none of the caller's data */
+int fea_gpu_flush_l2(fea_gpu_handle h);
+
+/* ---- host-only planning (no CUDA calls; testable on a CPU box) --------- */
+
+/* partition + symbolic phase exactly as fea_gpu_create runs it */
+int fea_plan_create(fea_plan_handle *out, int32_t n_nodes, int32_t n_elems,
+                    const double *X0, const int32_t *conn, int32_t rank, int32_t nranks);
+int fea_plan_destroy(fea_plan_handle p);
+/* same slots as fea_gpu_counts */
+int fea_plan_counts(fea_plan_handle p, int64_t out[16]);
+/* any pointer may be NULL.
+ *   local_node_gid  [local nodes]      global id of each local node (owned first)
+ *   local_elem_gid  [local elements]
+ *   browptr         [owned nodes + 1]  block-row pointers
+ *   bcol            [nnzb]             local column node ids, ascending
+ *   cptr            [nnzb + 1], csrc [contributions]  gather map (element-ascending);
+ *                   csrc = elem*55 + tri(a,b) | (1<<31 if the stored block is transposed)
+ *   nbr_rank [nbr], send_ptr [nbr+1], send_nodes [sent] (local ids), recv_ptr [nbr+1]
+ *                   (ghost offset ranges, in local numbering minus owned count) */
+int fea_plan_arrays(fea_plan_handle p, int32_t *local_node_gid, int32_t *local_elem_gid,
+                    int32_t *browptr, int32_t *bcol, int32_t *cptr, uint32_t *csrc,
+                    int32_t *nbr_rank, int32_t *send_ptr, int32_t *send_nodes,
+                    int32_t *recv_ptr);
+int fea_plan_node_owner(fea_plan_handle p, int32_t *owner /* [n_nodes] */);
+
+/* Kuhn (Freudenthal) 6-tet block, 10-node tets in the reference node order:
+ * nx*ny*nz cubes on [0,lx]x[y0,y0+ly]x[0,lz]; nodes (2nx+1)(2ny+1)(2nz+1), tets 6*nx*ny*nz.
+ * Call with NULL arrays for sizes.  bc_style 0 = "analytical" (face y=y0: type 2 value 0
+ * plus one corner type 7; face y=y0+ly: type 2 value dy), 1 = clamped (type 7 on both). */
+int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz,
+                   double y0, int32_t bc_style, double dy, int64_t *n_nodes,
+                   int64_t *n_elems, int64_t *n_presc, double *nodes, int32_t *conn,
+                   int32_t *presc_node, int32_t *presc_type, double *presc_vals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEA_GPU_H */

@@ -1,0 +1,61 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "fea-large_b200", "python"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BRICKS = ["neohook_brick", "a5_brick", "neohook_brick_analytical", "a5_brick_analytical"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_checkers():
+    """Build the CPU oracle (and, where /root/reference exists, oracle/_ref)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port", "ref"], check=True)
+    lib = os.path.join(ROOT, "fea-large_b200", "lib", "libfea_gpu.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "fea-large_b200"), "lib"], check=True)
+
+
+def load_golden(name):
+    from oracle.oracle import Model
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m = Model(nodes=np.ascontiguousarray(z["nodes"]), conn=np.ascontiguousarray(z["conn"]),
+              presc_node=np.ascontiguousarray(z["presc_node"]), presc_type=np.ascontiguousarray(z["presc_type"]),
+              presc_vals=np.ascontiguousarray(z["presc_vals"]), model=int(z["model"]), lam=float(z["lam"]),
+              mu=float(z["mu"]), gauss=int(z["gauss"]), load_increments=120,
+              desired_tolerance=float(z["desired_tolerance"]), modified_newton=bool(z["modified_newton"]),
+              max_newton=int(z["max_newton"]), solver_type=int(z["solver_type"]))
+    return m, z
+
+
+@pytest.fixture(params=BRICKS)
+def brick(request):
+    m, z = load_golden(request.param)
+    return request.param, m, z
+
+
+def csr_mv(rp, ci, v, x):
+    y = np.zeros(len(rp) - 1)
+    np.add.at(y, np.repeat(np.arange(len(rp) - 1), np.diff(rp)), v * x[ci])
+    return y
+
+
+def block_model(n, model=1, bc_style=0, dy=0.0, box=(1.0, 1.0, 1.0), y0=0.0):
+    """Kuhn block as an oracle Model (uses the product's host mesh generator)."""
+    import fea_gpu as fg
+    from oracle.oracle import Model
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    mb = fg.mesh_block(nx, ny, nz, box[0], box[1], box[2], y0, bc_style, dy)
+    return Model(nodes=mb["nodes"], conn=mb["conn"], presc_node=mb["presc_node"], presc_type=mb["presc_type"],
+                 presc_vals=mb["presc_vals"], model=model, lam=100.0, mu=100.0, gauss=5)

@@ -1,0 +1,259 @@
+"""GPU (B200): the CUDA hot path, called through the C-ABI, against the CPU oracle on the
+reference's shipped bricks and on synthetic Kuhn blocks.
+
+Tolerances (FP64, stated once):
+  RTOL_ELEM  = 1e-12  element-level quantities F, sigma, K entries, R (relative to the
+                      largest magnitude of the compared array) -- the CUDA path uses FMA and
+                      a closed form of the symmetrised tangent, so it is not bitwise.
+  RTOL_SOLVE = 1e-9   displacements after a linear solve / Newton iterate (both sides solve
+                      K u = R to ~1e-14 relative residual; cond(K) ~ 1e5).
+"""
+import numpy as np
+import pytest
+
+import fea_gpu as fg
+from conftest import block_model, csr_mv, load_golden
+from oracle.oracle import PortOracle, uniaxial_a5, uniaxial_neohookean
+
+pytestmark = pytest.mark.gpu
+RTOL_ELEM = 1e-12
+RTOL_SOLVE = 1e-9
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make_gpu(m, **kw):
+    return fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, m.gauss, m.presc_node, m.presc_type, m.presc_vals, **kw)
+
+
+def deformed(m, seed=11, amp=0.01):
+    rng = np.random.default_rng(seed)
+    return m.nodes + amp * rng.standard_normal(m.nodes.shape)
+
+
+def test_loaded_native_library():
+    assert fg.lib() is not None
+    n0 = fg.launch_count()
+    m, _ = load_golden("neohook_brick")
+    g = make_gpu(m); g.update_state(); g.sync()
+    assert fg.launch_count() > n0
+
+
+def test_state_stiffness_residual_vs_oracle(brick):
+    name, m, z = brick
+    g, o = make_gpu(m), PortOracle(m)
+    x = deformed(m)
+    for s in (g, o):
+        s.set_nodes(x); s.apply_increment(1.0); s.update_state(); s.assemble_stiffness(); s.assemble_residual()
+    assert relmax(g.get_nodes(), o.get_nodes()) == 0.0
+    Fg, Sg = g.get_state(); Fo, So = o.get_state()
+    assert relmax(Fg, Fo) < RTOL_ELEM and relmax(Sg, So) < RTOL_ELEM
+    rows, rp, ci, v = g.get_csr()
+    rpo, cio, vo = o.get_csr()
+    assert np.array_equal(rows, np.arange(m.n_dof))
+    assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)      # pattern identical, ascending, int32
+    assert len(v) == 145737 and rp.dtype == np.int32 and ci.dtype == np.int32
+    assert relmax(v, vo) < RTOL_ELEM
+    assert relmax(g.get_forces(), o.get_forces()) < RTOL_ELEM
+    assert g.bad_points() == 0
+
+
+def test_against_committed_golden(brick):
+    """Same checks against the fixtures written by the reference's compiled code."""
+    name, m, z = brick
+    g = make_gpu(m)
+    g.apply_increment(1.0); g.update_state(); g.assemble_stiffness(); g.assemble_residual()
+    F, S = g.get_state()
+    assert relmax(F, z["F"]) < RTOL_ELEM and relmax(S, z["S"]) < RTOL_ELEM
+    assert relmax(g.get_forces(), z["R"]) < RTOL_ELEM
+    for p, kv in zip(z["probes"], z["Kv"]):
+        assert relmax(g.spmv(p), kv) < RTOL_ELEM
+    g.apply_bc(0.0)
+    assert relmax(g.get_forces(), z["R_bc"]) < RTOL_ELEM
+    for p, kv in zip(z["probes"], z["Kv_bc"]):
+        assert relmax(g.spmv(p), kv) < RTOL_ELEM
+    it, rr, ok = g.solve(1e-14, 20000)
+    assert ok and relmax(g.get_solution(), z["u_first"]) < RTOL_SOLVE
+
+
+def test_fused_pass_equals_phase_calls(brick):
+    name, m, _ = brick
+    a, b = make_gpu(m), make_gpu(m)
+    x = deformed(m, 5)
+    for s in (a, b):
+        s.set_nodes(x)
+    a.update_state(); a.assemble_stiffness(); a.assemble_residual()
+    b.assemble_all(True)
+    assert np.array_equal(a.get_csr()[3], b.get_csr()[3])
+    assert np.array_equal(a.get_forces(), b.get_forces())
+    assert all(np.array_equal(p, q) for p, q in zip(a.get_state(), b.get_state()))
+
+
+def test_assembly_is_bit_reproducible():
+    m, _ = load_golden("a5_brick")
+    g = make_gpu(m)
+    g.set_nodes(deformed(m, 2))
+    g.assemble_all(True); v1, r1 = g.get_csr()[3].copy(), g.get_forces().copy()
+    for _ in range(3):
+        g.assemble_all(True)
+        assert np.array_equal(g.get_csr()[3], v1) and np.array_equal(g.get_forces(), r1)
+    h = make_gpu(m); h.set_nodes(deformed(m, 2)); h.assemble_all(True)
+    assert np.array_equal(h.get_csr()[3], v1)
+
+
+def test_bc_cancellation_and_rhs(brick):
+    name, m, _ = brick
+    for lam in (0.0, 0.5):
+        g, o = make_gpu(m), PortOracle(m)
+        x = deformed(m, 3)
+        for s in (g, o):
+            s.set_nodes(x); s.update_state(); s.assemble_stiffness(); s.assemble_residual(); s.apply_bc(lam)
+        assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+        assert relmax(g.get_forces(), o.get_forces()) < 10 * RTOL_ELEM
+
+
+def test_pcg_solution_and_start_vectors(brick):
+    name, m, _ = brick
+    g, o = make_gpu(m), PortOracle(m)
+    for s in (g, o):
+        s.apply_increment(1.0); s.update_state(); s.assemble_stiffness(); s.assemble_residual(); s.apply_bc(0.0)
+    o.solve_slae()
+    uo = o.get_solution()
+    it0, rr0, ok0 = g.solve(1e-14, 20000, fg.X0_ZERO)
+    u0 = g.get_solution()
+    it1, rr1, ok1 = g.solve(1e-14, 20000, fg.X0_RHS)      # the reference's x0 = b start (fea_solver.c:251-256)
+    u1 = g.get_solution()
+    assert ok0 and ok1 and rr0 <= 1e-14 and rr1 <= 1e-14
+    assert relmax(u0, uo) < RTOL_SOLVE and relmax(u1, uo) < RTOL_SOLVE
+    rp, ci, v = o.get_csr()
+    res = csr_mv(rp, ci, v, u0) - o.get_forces()
+    assert np.linalg.norm(res) <= 1e-12 * np.linalg.norm(o.get_forces())
+    assert abs(g.dot_R_u() - o.dot_forces_solution()) <= 1e-9 * abs(o.dot_forces_solution())
+    # max_iter is honoured and reported
+    it, rr, ok = g.solve(1e-14, 5, fg.X0_ZERO, allow_unconverged=True)
+    assert not ok and it == 5
+
+
+def newton_gpu(g, load_increments, desired_tol, modified, max_newton, lin_tol=1e-14):
+    """The reference's solve() loop (fea_solver.c:163-236) driven through the C-ABI."""
+    us, tols = [], []
+    for step in range(load_increments):
+        it = 0
+        g.apply_increment(1.0); g.update_state(); g.assemble_stiffness(); g.save_stiffness()
+        while True:
+            it += 1
+            g.assemble_residual()
+            if modified:
+                g.restore_stiffness()
+            else:
+                g.assemble_stiffness()
+            g.apply_bc(0.0)
+            g.solve(lin_tol, 20000)
+            tol = g.dot_R_u()
+            us.append(g.get_solution()); tols.append(tol)
+            g.update_nodes(); g.update_state()
+            if not (abs(tol) > desired_tol and it < max_newton):
+                break
+        if it == max_newton:
+            break
+    return np.array(us), np.array(tols)
+
+
+def test_newton_trajectory_matches_reference_solve(brick):
+    """Every Newton iterate of the first two load increments against the trace of the
+    reference's own solve() (golden) -- same iteration counts, same <R,u>, same u."""
+    name, m, z = brick
+    g = make_gpu(m)
+    us, tols = newton_gpu(g, 2, m.desired_tolerance, m.modified_newton, m.max_newton)
+    assert len(us) == int(z["newton_count"])
+    assert np.allclose(tols, z["newton_tol"], rtol=1e-7, atol=1e-12)
+    assert relmax(us[:3], z["newton_u_head"]) < RTOL_SOLVE
+    assert relmax(us.sum(axis=0), z["newton_u_sum"]) < RTOL_SOLVE
+    o = PortOracle(m)
+    o.newton_solve(2, m.desired_tolerance, m.modified_newton, m.max_newton)
+    assert relmax(g.get_nodes() - m.nodes, o.get_nodes() - m.nodes) < RTOL_SOLVE
+    assert relmax(g.get_state()[1], o.get_state()[1]) < 1e-8
+
+
+@pytest.mark.parametrize("name,closed", [("neohook_brick_analytical", uniaxial_neohookean),
+                                         ("a5_brick_analytical", uniaxial_a5)])
+def test_uniaxial_exact_solution(name, closed):
+    """exact-solutions/uniaxial: full Newton at a tight tolerance lands on the closed form."""
+    m, _ = load_golden(name)
+    g = make_gpu(m)
+    newton_gpu(g, 1, 1e-22, False, 60)
+    F, S = g.get_state()
+    k1 = 1 + 0.05 / 6
+    k2, sig = closed(k1)
+    assert np.allclose(S[:, :, 1, 1], sig, rtol=1e-9)
+    assert np.allclose(F[:, :, 1, 1], k1, rtol=1e-10) and np.allclose(F[:, :, 0, 0], k2, rtol=1e-9)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("ng", [4, 5])
+def test_kuhn_block_vs_oracle(model, ng):
+    m = block_model((3, 4, 3), model=model, dy=0.02)
+    m.gauss = ng
+    g, o = make_gpu(m), PortOracle(m)
+    x = deformed(m, 9, 0.004)
+    for s in (g, o):
+        s.set_nodes(x); s.apply_increment(1.0); s.update_state(); s.assemble_stiffness(); s.assemble_residual()
+    assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+    assert np.array_equal(g.get_csr()[2], o.get_csr()[1])
+    assert relmax(g.get_forces(), o.get_forces()) < RTOL_ELEM
+    assert relmax(g.get_state()[1], o.get_state()[1]) < RTOL_ELEM
+
+
+def test_ragged_tail_and_tiny_meshes():
+    for n in [(1, 1, 1), (1, 2, 1), (2, 3, 2)]:          # 6, 12, 72 elements: partial CTAs
+        m = block_model(n, model=1)
+        g, o = make_gpu(m), PortOracle(m)
+        x = deformed(m, 1, 0.01)
+        for s in (g, o):
+            s.set_nodes(x); s.update_state(); s.assemble_stiffness(); s.assemble_residual()
+        assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+        assert relmax(g.get_forces(), o.get_forces()) < RTOL_ELEM
+
+
+def test_inverted_elements_are_counted_not_hidden():
+    m = block_model((2, 2, 2), model=1)
+    g = make_gpu(m)
+    x = m.nodes.copy(); x[:, 1] *= -1.0               # mirror: det J < 0 everywhere, |det J| is used (:958)
+    g.set_nodes(x); g.assemble_all(True)
+    assert g.bad_points() == 5 * len(m.conn)
+    o = PortOracle(m); o.set_nodes(x); o.update_state(); o.assemble_stiffness()
+    assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+
+
+def test_large_block_properties():
+    """Size-independent properties at a size the oracle cannot reach in seconds (N=24:
+    82 944 tets, 352 947 DOF): symmetry, rigid-body null space, zero residual at rest,
+    homogeneous uniaxial stretch = closed form, PCG residual."""
+    n = 24
+    m = block_model(n, model=1, bc_style=1, dy=0.01)
+    g = make_gpu(m)
+    g.assemble_all(True)
+    assert np.abs(g.get_forces()).max() < 1e-12                      # undeformed: R = 0
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(m.n_dof), rng.standard_normal(m.n_dof)
+    assert abs(a @ g.spmv(b) - b @ g.spmv(a)) < 1e-11 * abs(a @ g.spmv(b))
+    t = np.tile([1.0, -2.0, 0.5], len(m.nodes))
+    assert np.abs(g.spmv(t)).max() < 1e-9 * np.abs(g.spmv(b)).max()  # translations in the null space
+    k1 = 1.5
+    k2, sig = uniaxial_neohookean(k1)
+    x = m.nodes * np.array([k2, k1, k2])
+    g.set_nodes(x); g.assemble_all(True)
+    F, S = g.get_state()
+    assert np.allclose(S[:, :, 1, 1], sig, rtol=1e-10) and np.abs(S[:, :, 0, 0]).max() < 1e-9
+    R = g.get_forces().reshape(-1, 3)
+    interior = (np.abs(m.nodes[:, 1]) > 1e-9) & (np.abs(m.nodes[:, 1] - 1) > 1e-9) & \
+               (np.abs(m.nodes[:, 0]) > 1e-9) & (np.abs(m.nodes[:, 0] - 1) > 1e-9) & \
+               (np.abs(m.nodes[:, 2]) > 1e-9) & (np.abs(m.nodes[:, 2] - 1) > 1e-9)
+    assert np.abs(R[interior]).max() < 1e-10                          # equilibrium inside
+    g.set_nodes(m.nodes); g.apply_increment(1.0); g.assemble_all(True); g.apply_bc(0.0)
+    it, rr, ok = g.solve(1e-10, 20000)
+    u, Rb = g.get_solution(), g.get_forces()
+    assert ok and np.linalg.norm(g.spmv(u) - Rb) <= 2e-10 * np.linalg.norm(Rb)
+    assert g.counts()["nnzb"] * 9 / m.n_dof > 80                      # ~81-86 nnz/row

@@ -1,0 +1,132 @@
+"""CPU: host-side partition + symbolic phase (fea_plan_*), checked against the oracle's
+assembled matrix and by simulating the gather map with numpy."""
+import numpy as np
+import pytest
+
+import fea_gpu as fg
+from conftest import block_model, csr_mv, load_golden
+from oracle.oracle import PortOracle
+
+TRI = {(a, b): a * 10 - (a * (a - 1)) // 2 + (b - a) for a in range(10) for b in range(a, 10)}
+
+
+def staged_blocks(o, n_elems):
+    """[e][55][3][3] upper-triangular node-pair blocks of the oracle's K_e."""
+    out = np.zeros((n_elems, 55, 3, 3))
+    for e in range(n_elems):
+        ke = o.element_matrix(e).reshape(10, 3, 10, 3)
+        for (a, b), t in TRI.items():
+            out[e, t] = ke[a, :, b, :]
+    return out
+
+
+def gather_numpy(plan, staged):
+    """What gather_blocks_kernel computes, in numpy."""
+    flat = staged.reshape(-1, 3, 3)
+    idx = (plan.csrc & 0x7fffffff).astype(np.int64)
+    tr = (plan.csrc >> 31).astype(bool)
+    blocks = flat[idx]
+    blocks[tr] = blocks[tr].transpose(0, 2, 1)
+    vals = np.zeros((plan.nnzb, 3, 3))
+    np.add.at(vals, np.repeat(np.arange(plan.nnzb), np.diff(plan.cptr)), blocks)
+    return vals
+
+
+def bsr_to_dense_rows(plan, vals, n_dof):
+    A = np.zeros((3 * plan.n_own, n_dof))
+    for I in range(plan.n_own):
+        for k in range(plan.browptr[I], plan.browptr[I + 1]):
+            J = plan.node_gid[plan.bcol[k]]
+            A[3 * I:3 * I + 3, 3 * J:3 * J + 3] = vals[k]
+    return A
+
+
+def test_pattern_and_gather_map_reproduce_oracle_matrix():
+    m, z = load_golden("neohook_brick")
+    o = PortOracle(m)
+    o.apply_increment(1.0); o.update_state(); o.assemble_stiffness()
+    rp, ci, v = o.get_csr()
+    p = fg.Plan(m.nodes, m.conn)
+    assert p.nnzb * 9 == len(v) == 145737
+    for I in range(p.n_own):   # full 3x3 blocks, ascending columns, identical node sets
+        assert np.array_equal(p.node_gid[p.bcol[p.browptr[I]:p.browptr[I + 1]]], ci[rp[3 * I]:rp[3 * I + 1]][::3] // 3)
+    vals = gather_numpy(p, staged_blocks(o, len(m.conn)))
+    A = bsr_to_dense_rows(p, vals, m.n_dof)
+    Aref = np.zeros_like(A)
+    Aref[np.repeat(np.arange(m.n_dof), np.diff(rp)), ci] = v
+    assert np.abs(A - Aref).max() <= 1e-13 * np.abs(Aref).max()
+    # contributions are element-ascending within each nonzero (deterministic order)
+    e_of = (p.csrc & 0x7fffffff) // 55
+    for k in range(0, p.nnzb, 97):
+        seg = e_of[p.cptr[k]:p.cptr[k + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) >= 0)
+
+
+def test_kuhn_block_counts_and_geometry():
+    n = 6
+    mb = fg.mesh_block(n, n, n)
+    assert mb["nodes"].shape == ((2 * n + 1) ** 3, 3) and mb["conn"].shape == (6 * n ** 3, 10)
+    assert len(np.unique(mb["conn"])) == (2 * n + 1) ** 3          # every half-grid point is used
+    X = mb["nodes"][mb["conn"]]
+    for k, (a, b) in enumerate([(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]):   # fea_solver.c:1295-1300
+        assert np.abs(X[:, 4 + k] - (X[:, a] + X[:, b]) / 2).max() < 1e-15
+    m = block_model(n)
+    o = PortOracle(m); o.update_state()
+    g, detJ = o.get_gradients()
+    assert detJ.min() > 0 and np.isclose((detJ * PortOracle.tables(5)[0][:, 0]).sum(), 1.0, rtol=1e-12)
+    p = fg.Plan(m.nodes, m.conn)
+    assert np.diff(p.browptr).max() * 3 == 195                     # max row of Kuhn meshes
+    assert 2.2 < p.n_contrib / p.nnzb < 2.7
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_partition_halo_lists_are_consistent(nranks):
+    m = block_model((3, 8, 3))
+    plans = [fg.Plan(m.nodes, m.conn, r, nranks) for r in range(nranks)]
+    owner = plans[0].owner
+    assert sum(p.n_own for p in plans) == len(m.nodes)
+    assert np.abs(np.bincount(owner, minlength=nranks) - len(m.nodes) / nranks).max() <= 1
+    f = lambda gid: 1000.0 + 3.0 * gid                      # noqa: E731  value carried by node gid
+    for r, p in enumerate(plans):
+        assert np.all(owner[p.node_gid[:p.n_own]] == r) and np.all(np.diff(p.node_gid[:p.n_own]) > 0)
+        # every element touching an owned node is local, with all its nodes present
+        touch = np.where((owner[m.conn] == r).any(axis=1))[0]
+        assert np.array_equal(touch, p.elem_gid)
+        assert set(np.unique(m.conn[touch])) == set(p.node_gid)
+        for i, q in enumerate(p.nbr_rank):
+            pq = plans[q]
+            j = list(pq.nbr_rank).index(r)
+            sent = p.node_gid[p.send_nodes[p.send_ptr[i]:p.send_ptr[i + 1]]]
+            ghosts = pq.node_gid[pq.n_own + pq.recv_ptr[j]: pq.n_own + pq.recv_ptr[j + 1]]
+            assert np.array_equal(sent, ghosts)               # same nodes, same order on both sides
+            assert np.array_equal(f(sent), f(ghosts))
+        assert p.recv_ptr[-1] == p.n_local - p.n_own
+
+
+def test_distributed_rows_reassemble_global_matrix():
+    m = block_model((2, 4, 2), model=0)
+    o = PortOracle(m)
+    rng = np.random.default_rng(3)
+    o.set_nodes(m.nodes + 0.01 * rng.standard_normal(m.nodes.shape))
+    o.update_state(); o.assemble_stiffness()
+    rp, ci, v = o.get_csr()
+    x = rng.standard_normal(m.n_dof)
+    y_ref = csr_mv(rp, ci, v, x)
+    y = np.zeros(m.n_dof)
+    for r in range(3):
+        p = fg.Plan(m.nodes, m.conn, r, 3)
+        oo = PortOracle(type(m)(**{**m.__dict__, "conn": np.ascontiguousarray(m.conn[p.elem_gid])}))
+        oo.set_nodes(o.get_nodes()); oo.update_state()
+        vals = gather_numpy(p, staged_blocks(oo, p.n_elems))   # element ids are local here
+        A = bsr_to_dense_rows(p, vals, m.n_dof)
+        rows = (3 * p.node_gid[:p.n_own, None] + np.arange(3)).ravel()
+        y[rows] = A @ x
+    assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+
+
+def test_bad_meshes_are_rejected():
+    mb = fg.mesh_block(1, 1, 1)
+    conn = mb["conn"].copy(); conn[0, 0] = 10 ** 6
+    with pytest.raises(fg.FeaGpuError) as e:
+        fg.Plan(mb["nodes"], conn)
+    assert e.value.code == fg.ERR_MESH
