@@ -76,6 +76,7 @@ struct fea_gpu_ctx {
   int64_t nnzb = 0;
   int spmv_lpr = 16;
   int pcg_batch = 32;
+  int pcg_stall = 0;               // 0 = automatic
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;
@@ -100,6 +101,7 @@ struct fea_gpu_ctx {
   unsigned long long *bad = nullptr;
   void *flush = nullptr;
   double *export_buf = nullptr;    // lazily allocated [n_elems][ng][9]
+  double *stage_h = nullptr;       // pinned staging for the multi-rank host-buffer path
 
   cudaEvent_t ev_a[PH_COUNT], ev_b[PH_COUNT];
   bool ev_set[PH_COUNT];
@@ -410,6 +412,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
+  if (c->stage_h) cudaFreeHost(c->stage_h);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return FEA_GPU_OK;
@@ -690,6 +693,12 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
 
   fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->diag, c->dinv);
   LAUNCHED();
+  {
+    // PCG's ||r|| is not monotone and plateaus grow with the mesh: scale the window
+    const double ndof = 3.0 * (double)c->plan.n_nodes_global;
+    const int stall_limit = c->pcg_stall > 0 ? c->pcg_stall : std::max(200, (int)(10.0 * std::cbrt(ndof)));
+    CU(cudaMemcpyAsync(&c->ctl->stall_limit, &stall_limit, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
   if (flags & FEA_SOLVE_X0_RHS) {
     CU(cudaMemcpyAsync(c->u, c->R, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     TRY(halo_exchange(c, c->u));
@@ -848,6 +857,55 @@ extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, 
 }
 
 // ---------------------------------------------------------------------------------
+// host-buffer path (end-to-end step)
+
+extern "C" int fea_gpu_host_alloc(void **out, uint64_t bytes) {
+  if (!out) return FEA_GPU_ERR_ARG;
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_host_free(void *p) {
+  if (p) CU(cudaFreeHost(p));
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t with_stiffness, double *R,
+                                      uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+  CHECK_H(c);
+  if (!x || !R) return FEA_GPU_ERR_ARG;
+  const fea::Plan &pl = c->plan;
+  const size_t nl3 = 3 * (size_t)c->n_local, n3 = 3 * (size_t)c->n_own;
+  if (pl.nranks == 1) {
+    // local numbering == global numbering: DMA straight from / to the caller's arrays
+    CU(cudaMemcpyAsync(c->x, x, sizeof(double) * nl3, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (!c->stage_h) CU(cudaHostAlloc((void **)&c->stage_h, sizeof(double) * nl3, cudaHostAllocDefault));
+    for (int32_t l = 0; l < c->n_local; ++l)
+      std::memcpy(c->stage_h + 3 * (size_t)l, x + 3 * (size_t)pl.node_gid[(size_t)l], 3 * sizeof(double));
+    CU(cudaMemcpyAsync(c->x, c->stage_h, sizeof(double) * nl3, cudaMemcpyHostToDevice, c->stream));
+  }
+  TRY(element_pass(c, with_stiffness != 0, true));
+  if (with_stiffness) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, c->pflag);   // prescribed rows -> 0 (lambda = 0)
+  LAUNCHED();
+  phase_end(c, PH_GATHER_R);
+  if (pl.nranks == 1) {
+    CU(cudaMemcpyAsync(R, c->R, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } else {
+    CU(cudaMemcpyAsync(c->stage_h, c->R, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int32_t l = 0; l < c->n_own; ++l)
+      std::memcpy(R + 3 * (size_t)pl.node_gid[(size_t)l], c->stage_h + 3 * (size_t)l, 3 * sizeof(double));
+  }
+  if (h2d_bytes) *h2d_bytes = sizeof(double) * nl3;
+  if (d2h_bytes) *d2h_bytes = sizeof(double) * n3;
+  return FEA_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // introspection / measurement
 
 extern "C" int fea_gpu_counts(fea_gpu_handle c, int64_t out[16]) {
@@ -894,6 +952,20 @@ extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
   out[PH_SPMV] = c->sp_used ? sp / c->sp_used : 0.0;  // average ms per in-solve SpMV launch
   out[8] = c->sp_used;
   out[9] = c->last_iters;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double value) {
+  if (!c || !name) return FEA_GPU_ERR_ARG;
+  const std::string k(name);
+  const int v = (int)value;
+  if (k == "spmv_lpr" && (v == 4 || v == 8 || v == 16 || v == 32)) c->spmv_lpr = v;
+  else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
+  else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
+  else {
+    g_err = "unknown parameter or value out of range: " + k;
+    return FEA_GPU_ERR_ARG;
+  }
   return FEA_GPU_OK;
 }
 

@@ -182,8 +182,11 @@ struct PcgCtl {
   double bb;        // b . b
   double thresh;    // stop when rr <= thresh
   double beta;
-  int done;
+  double best_rr;   // smallest r.r seen so far (stagnation guard)
+  int done;         // 1 = tolerance met, 2 = stalled at the rounding floor
   int iters;
+  int stall;        // iterations since best_rr last improved
+  int stall_limit;
 };
 
 template <int LPR, bool FUSE_DOT>
@@ -260,6 +263,8 @@ pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ 
     ctl->rr = s[2];
     ctl->iters = 0;
     ctl->beta = 0.0;
+    ctl->stall = 0;
+    ctl->best_rr = s[2];
     if (finalize) {
       ctl->thresh = abs_tol ? tol * tol : tol * tol * s[1];
       ctl->done = (s[1] == 0.0 || s[2] <= ctl->thresh) ? 1 : 0;
@@ -270,6 +275,7 @@ pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ 
 // multi-rank: fold the all-reduced sums of pcg_init into the control block
 __global__ void pcg_init_finalize_kernel(PcgCtl *ctl, double tol, int abs_tol) {
   ctl->rz_old = ctl->rz_new;
+  ctl->best_rr = ctl->rr;
   ctl->thresh = abs_tol ? tol * tol : tol * tol * ctl->bb;
   ctl->done = (ctl->bb == 0.0 || ctl->rr <= ctl->thresh) ? 1 : 0;
 }
@@ -279,6 +285,14 @@ __device__ __forceinline__ void pcg_step_control(PcgCtl *ctl) {
   ctl->rz_old = ctl->rz_new;
   ctl->iters += 1;
   if (ctl->rr <= ctl->thresh || !(ctl->rr == ctl->rr)) ctl->done = 1;
+  // the residual norm has not improved for stall_limit iterations: r is at the rounding
+  // floor of this system (typical for the last Newton iterations, where b itself is tiny)
+  if (ctl->rr < 0.999 * ctl->best_rr) {
+    ctl->best_rr = ctl->rr;
+    ctl->stall = 0;
+  } else if (++ctl->stall >= ctl->stall_limit && !ctl->done) {
+    ctl->done = 2;
+  }
 }
 
 // u += alpha p; r -= alpha q; sums r.(dinv r), r.r.  With `finalize` (single rank) the last

@@ -33,7 +33,7 @@ SYMBOLS = [
     "fea_gpu_set_forces", "fea_gpu_get_solution", "fea_gpu_get_csr", "fea_gpu_bad_points",
     "fea_gpu_counts", "fea_gpu_launch_count", "fea_gpu_timer_start", "fea_gpu_timer_stop",
     "fea_gpu_sync", "fea_gpu_phase_ms", "fea_gpu_bench_spmv", "fea_gpu_measure_peaks",
-    "fea_gpu_flush_l2", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
+    "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
     "fea_plan_node_owner", "fea_mesh_block",
 ]
 
@@ -94,6 +94,16 @@ def mesh_block(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, y0=0.0, bc_style=0, dy=0.0):
     _check(f(nx, ny, nz, lx, ly, lz, y0, bc_style, dy, None, None, None, nodes.ctypes.data, conn.ctypes.data,
              pn.ctypes.data, pt.ctypes.data, pv.ctypes.data))
     return dict(nodes=nodes, conn=conn, presc_node=pn, presc_type=pt, presc_vals=pv)
+
+
+def host_array(shape, dtype=np.float64):
+    """numpy array backed by page-locked memory from fea_gpu_host_alloc (never freed: bench use)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    lib().fea_gpu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    _check(lib().fea_gpu_host_alloc(C.byref(p), n))
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 class Plan:
@@ -295,6 +305,18 @@ class FeaGpu:
         d["spmv_samples"] = int(out[8])
         d["pcg_iters"] = int(out[9])
         return d
+
+    def set_param(self, name, value):
+        lib().fea_gpu_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        _check(lib().fea_gpu_set_param(self.h, name.encode(), float(value)))
+
+    def step_from_host(self, x, R, with_stiffness=True):
+        """fea_gpu_step_from_host: x, R are host arrays (ideally from host_array()); returns bytes moved."""
+        f = lib().fea_gpu_step_from_host
+        f.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(f(self.h, x, int(with_stiffness), R, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def bench_spmv(self, reps=20) -> float:
         ms = C.c_double(0)

@@ -109,6 +109,8 @@ int fea_gpu_restore_stiffness(fea_gpu_handle h);
 /* ---- linear solve and Newton bookkeeping ------------------------------- */
 
 /* solver_solve_slae (:300-321): Jacobi-preconditioned CG on K u = R.
+ * Stops when ||r|| <= tol ||b|| (or tol, FEA_SOLVE_ABS_TOL), or when ||r|| has not
+ * improved for 200 iterations (rounding floor; still FEA_GPU_OK, relres tells).
  * iters/relres may be NULL.  Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter. */
 int fea_gpu_solve(fea_gpu_handle h, double tol, int32_t max_iter, int32_t flags,
                   int32_t *iters, double *relres);
@@ -133,6 +135,21 @@ int fea_gpu_get_csr(fea_gpu_handle h, int64_t *n_rows, int64_t *nnz, int32_t *ro
 /* elements whose |J| or det F was <= 0 (or J singular) in the last element pass */
 int fea_gpu_bad_points(fea_gpu_handle h, int64_t *count);
 
+/* ---- host-buffer (end-to-end) path --------------------------------------- */
+
+/* page-locked host memory for the arrays the host layer hands to the calls below
+ * (nodes_p, global_forces_vct, ...), so copies are direct DMA */
+int fea_gpu_host_alloc(void **out, uint64_t bytes);
+int fea_gpu_host_free(void *p);
+/* One assembly pass driven from HOST arrays, as the reference's phase sequence
+ * solver_create_current_shape_gradients + _stresses + _stiffness + _residual_forces +
+ * solver_apply_prescribed_bc(0) (fea_solver.c:171-203) would be with host-resident nodes:
+ * copies x [n_nodes][3] host->device, runs the element pass, gathers, cancels BC rows,
+ * copies global_forces_vct (this rank's rows; all rows when nranks == 1) device->host.
+ * h2d_bytes / d2h_bytes (may be NULL) report what crossed the bus. */
+int fea_gpu_step_from_host(fea_gpu_handle h, const double *x, int32_t with_stiffness,
+                           double *R, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+
 /* ---- introspection / measurement --------------------------------------- */
 
 /* out[0]=owned nodes, [1]=local nodes (owned+ghost), [2]=local elements,
@@ -153,6 +170,10 @@ int fea_gpu_phase_ms(fea_gpu_handle h, double out[16]);
 int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);
 /* measured machine peaks on this device: FP64 FMA TFLOP/s, copy GB/s (read+write) */
 int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs);
+/* tuning knobs: "spmv_lpr" (lanes per block row: 4, 8, 16, 32), "pcg_batch" (iterations
+ * queued between host convergence checks), "pcg_stall" (iterations without a new best
+ * ||r|| before PCG declares the rounding floor; 0 = automatic, max(200, 10 n^(1/3))) */
+int fea_gpu_set_param(fea_gpu_handle h, const char *name, double value);
 /* overwrite >= `bytes` of scratch so L2 holds none of the caller's data */
 int fea_gpu_flush_l2(fea_gpu_handle h);
 
