@@ -28,6 +28,7 @@ namespace fea {
 
 constexpr int ELEMS_PER_CTA = 32;
 constexpr int NFIELD = 62;  // g[3][10], t[3][10], lam', mu'
+constexpr int TILE_LD = 19;  // per-lane pitch of the store-transpose tile (odd: conflict-free)
 
 struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
@@ -70,8 +71,8 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
 }
 
 template <int MODEL, int NG, bool WITH_K, bool WITH_R>
-__global__ void __launch_bounds__(NG * 32) element_kernel(ElemArgs A) {
-  extern __shared__ double sm[];  // [NG][NFIELD][32]
+__global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
+  extern __shared__ double sm[];  // [NG][NFIELD][32] fields, then [NG][32][TILE_LD] store tiles
   const int lane = threadIdx.x & 31;
   const int gp = threadIdx.x >> 5;
   const int e = blockIdx.x * ELEMS_PER_CTA + lane;
@@ -223,46 +224,77 @@ __global__ void __launch_bounds__(NG * 32) element_kernel(ElemArgs A) {
   }
 
   if (WITH_K) {
+    // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- consecutive in
+    // the packed upper triangle, i.e. 144 contiguous bytes of K_e staging -- then the warp
+    // transposes them through a padded tile so its stores walk those 144-byte chunks with
+    // consecutive lanes (8-byte stores at a 3960-byte lane stride cost 27 L2 sectors per
+    // request in v1; see profiles/r1_v1_ncu_full_summary.md).
+    double *tile = sm + (size_t)NG * NFIELD * 32 + (size_t)gp * 32 * TILE_LD;
+    const int e0 = blockIdx.x * ELEMS_PER_CTA;
     // rows a and 9-a of the upper triangle hold 11 blocks together: one such pair per warp
     // when NG == 5 (pairs are dealt round-robin otherwise)
     for (int pr = gp; pr < 5; pr += NG)
-    for (int half = 0; half < 2; ++half) {
-      const int a = half ? 9 - pr : pr;
-      double ga[NG][3], ua[NG][3], va[NG][3];
-#pragma unroll
-      for (int q = 0; q < NG; ++q) {
-        const double lw = FLD(q, 60), mw = FLD(q, 61);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          ga[q][i] = FLD(q, i * 10 + a);
-          ua[q][i] = lw * ga[q][i];
-          va[q][i] = mw * ga[q][i];
-        }
-      }
-      for (int b = a; b < 10; ++b) {
-        double k[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int half = 0; half < 2; ++half) {
+        const int a = half ? 9 - pr : pr;
+        double ga[NG][3], ua[NG][3], va[NG][3];
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-          const double gb0 = FLD(q, b), gb1 = FLD(q, 10 + b), gb2 = FLD(q, 20 + b);
-          const double s = ga[q][0] * FLD(q, 30 + b) + ga[q][1] * FLD(q, 40 + b) + ga[q][2] * FLD(q, 50 + b);
-          const double gb[3] = {gb0, gb1, gb2};
+          const double lw = FLD(q, 60), mw = FLD(q, 61);
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              k[i][j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k[i][j]));
-          k[0][0] += s;
-          k[1][1] += s;
-          k[2][2] += s;
+          for (int i = 0; i < 3; ++i) {
+            ga[q][i] = FLD(q, i * 10 + a);
+            ua[q][i] = lw * ga[q][i];
+            va[q][i] = mw * ga[q][i];
+          }
         }
-        if (live) {
-          const int tri = a * 10 - (a * (a - 1)) / 2 + (b - a);
-          double *dst = A.Ke + ((size_t)e * 55 + tri) * 9;
+        for (int b = a; b < 10; b += 2) {
+          const bool two = b + 1 < 10;   // warp-uniform
+          double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-          for (int c = 0; c < 9; ++c) dst[c] = k[c / 3][c % 3];
+          for (int q = 0; q < NG; ++q) {
+            {
+              const double gb[3] = {FLD(q, b), FLD(q, 10 + b), FLD(q, 20 + b)};
+              const double s = ga[q][0] * FLD(q, 30 + b) + ga[q][1] * FLD(q, 40 + b) + ga[q][2] * FLD(q, 50 + b);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  k0[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
+              k0[0] += s;
+              k0[4] += s;
+              k0[8] += s;
+            }
+            if (two) {
+              const int b1 = b + 1;
+              const double gb[3] = {FLD(q, b1), FLD(q, 10 + b1), FLD(q, 20 + b1)};
+              const double s = ga[q][0] * FLD(q, 30 + b1) + ga[q][1] * FLD(q, 40 + b1) + ga[q][2] * FLD(q, 50 + b1);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  k1[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
+              k1[0] += s;
+              k1[4] += s;
+              k1[8] += s;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            tile[lane * TILE_LD + c] = k0[c];
+            tile[lane * TILE_LD + 9 + c] = k1[c];
+          }
+          __syncwarp();
+          const int tri = a * 10 - (a * (a - 1)) / 2 + (b - a);
+          const int nd = two ? 18 : 9;
+          for (int it = 0; it < nd; ++it) {
+            const int f = it * 32 + lane;
+            const int le = two ? f / 18 : f / 9;
+            const int cc = f - le * nd;
+            if (e0 + le < A.n_elems) A.Ke[((size_t)(e0 + le) * 55 + tri) * 9 + cc] = tile[le * TILE_LD + cc];
+          }
+          __syncwarp();
         }
       }
-    }
   }
 #undef FLD
 }

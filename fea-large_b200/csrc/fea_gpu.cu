@@ -74,14 +74,15 @@ struct fea_gpu_ctx {
   double lambda = 0, mu = 0;
   int n_own = 0, n_local = 0, n_elems = 0, ne_pad = 0;
   int64_t nnzb = 0;
-  int spmv_lpr = 16;
+  int64_t n_slots = 0;
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;
   double *F_soa = nullptr, *S_soa = nullptr, *Ke = nullptr, *Re = nullptr;
-  int32_t *browptr = nullptr, *bcol = nullptr, *cptr = nullptr, *rptr = nullptr, *rsrc = nullptr, *diag = nullptr;
+  int32_t *slice_ptr = nullptr, *sell_row = nullptr, *bcol = nullptr, *cptr = nullptr, *rptr = nullptr,
+          *rsrc = nullptr, *sdiag = nullptr;
   uint32_t *csrc = nullptr;
   double *vals = nullptr, *vals_saved = nullptr;
   double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr;
@@ -228,10 +229,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   c->n_elems = pl.n_elems;
   c->ne_pad = (pl.n_elems + 31) / 32 * 32;
   c->nnzb = pl.nnzb();
-  if (const char *s = getenv("FEA_SPMV_LPR")) {
-    int v = atoi(s);
-    if (v == 4 || v == 8 || v == 16 || v == 32) c->spmv_lpr = v;
-  }
+  c->n_slots = pl.n_slots();
   if (const char *s = getenv("FEA_PCG_BATCH")) {
     int v = atoi(s);
     if (v >= 1 && v <= 4096) c->pcg_batch = v;
@@ -266,13 +264,14 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
     TRY(dev_upload(&c->conn_soa, soa, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
-  TRY(dev_upload(&c->browptr, pl.browptr, c->stream));
-  TRY(dev_upload(&c->bcol, pl.bcol, c->stream));
-  TRY(dev_upload(&c->cptr, pl.cptr, c->stream));
-  TRY(dev_upload(&c->csrc, pl.csrc, c->stream));
+  TRY(dev_upload(&c->slice_ptr, pl.slice_ptr, c->stream));
+  TRY(dev_upload(&c->sell_row, pl.sell_row, c->stream));
+  TRY(dev_upload(&c->bcol, pl.sbcol, c->stream));
+  TRY(dev_upload(&c->cptr, pl.scptr, c->stream));
+  TRY(dev_upload(&c->csrc, pl.scsrc, c->stream));
   TRY(dev_upload(&c->rptr, pl.rptr, c->stream));
   TRY(dev_upload(&c->rsrc, pl.rsrc, c->stream));
-  TRY(dev_upload(&c->diag, pl.diag, c->stream));
+  TRY(dev_upload(&c->sdiag, pl.sdiag, c->stream));
   TRY(dev_upload(&c->send_nodes, pl.send_nodes, c->stream));
   TRY(dev_alloc(&c->send_buf, 3 * pl.send_nodes.size()));
 
@@ -320,7 +319,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_alloc(&c->S_soa, (size_t)c->ng * 9 * c->ne_pad));
   TRY(dev_alloc(&c->Ke, (size_t)c->n_elems * 55 * 9));
   TRY(dev_alloc(&c->Re, (size_t)30 * c->ne_pad));
-  TRY(dev_alloc(&c->vals, (size_t)c->nnzb * 9));
+  TRY(dev_alloc(&c->vals, (size_t)c->n_slots * 9));
   TRY(dev_alloc(&c->R, n3));
   TRY(dev_alloc(&c->u, nl3));
   TRY(dev_alloc(&c->p, nl3));
@@ -335,7 +334,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   CU(cudaHostAlloc((void **)&c->ctl_host, sizeof(PcgCtl), cudaHostAllocDefault));
   CU(cudaMemsetAsync(c->F_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
   CU(cudaMemsetAsync(c->S_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
-  CU(cudaMemsetAsync(c->vals, 0, sizeof(double) * (size_t)c->nnzb * 9, c->stream));
+  CU(cudaMemsetAsync(c->vals, 0, sizeof(double) * (size_t)c->n_slots * 9, c->stream));
   CU(cudaMemsetAsync(c->R, 0, sizeof(double) * n3, c->stream));
   CU(cudaMemsetAsync(c->u, 0, sizeof(double) * nl3, c->stream));
   CU(cudaMemsetAsync(c->p, 0, sizeof(double) * nl3, c->stream));
@@ -404,8 +403,8 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->has_comm) ncclCommDestroy(c->comm);
-  void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->browptr, c->bcol,
-                  c->cptr, c->rptr, c->rsrc, c->diag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
+  void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->slice_ptr, c->sell_row, c->bcol,
+                  c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->pflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
                   c->flush, c->export_buf};
@@ -453,10 +452,10 @@ static int gather_owned(fea_gpu_ctx *c, const double *dev_vec, double *host_glob
   std::vector<double> tmp(blk * (size_t)pl.nranks);
   CU(cudaMemcpyAsync(tmp.data(), rbuf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  std::vector<int32_t> pos((size_t)pl.nranks, 0);
-  for (int64_t g = 0; g < pl.n_nodes_global; ++g) {  // owned lists are ascending in global id
+  for (int64_t g = 0; g < pl.n_nodes_global; ++g) {  // every rank knows every owner's numbering
     const int o = pl.owner[(size_t)g];
-    std::memcpy(host_global + 3 * (size_t)g, tmp.data() + blk * (size_t)o + 3 * (size_t)pos[(size_t)o]++, 3 * sizeof(double));
+    std::memcpy(host_global + 3 * (size_t)g, tmp.data() + blk * (size_t)o + 3 * (size_t)pl.pos_in_owner[(size_t)g],
+                3 * sizeof(double));
   }
   cudaFree(sbuf);
   cudaFree(rbuf);
@@ -525,7 +524,7 @@ extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
 template <int MODEL, int NG>
 static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
   const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
-  const size_t smem = sizeof(double) * NG * fea::NFIELD * 32;
+  const size_t smem = sizeof(double) * NG * (fea::NFIELD + fea::TILE_LD) * 32;
 #define FEA_LAUNCH(K, Rr)                                                                          \
   do {                                                                                             \
     auto kern = fea::element_kernel<MODEL, NG, K, Rr>;                                             \
@@ -566,11 +565,21 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
   return rc;
 }
 
+static fea::SellMat sell_mat(fea_gpu_ctx *c) {
+  fea::SellMat A;
+  A.n_slices = c->plan.n_slices;
+  A.slice_ptr = c->slice_ptr;
+  A.sell_row = c->sell_row;
+  A.bcol = c->bcol;
+  A.vals = c->vals;
+  return A;
+}
+
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
-  const int grid = std::min(cdiv((int64_t)c->n_own * 32, 256), 148 * 16);
-  fea::gather_blocks_kernel<<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->cptr, c->csrc, c->Ke,
-                                                         c->vals, with_bc ? c->pflag : nullptr);
+  const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), 148 * 32);
+  fea::gather_blocks_kernel<<<grid, 256, 0, c->stream>>>(sell_mat(c), c->cptr, c->csrc, c->Ke,
+                                                         with_bc ? c->pflag : nullptr);
   LAUNCHED();
   phase_end(c, PH_GATHER_K);
   return FEA_GPU_OK;
@@ -620,24 +629,13 @@ extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
 // SpMV / BC / PCG
 
 static int launch_spmv(fea_gpu_ctx *c, const double *x, double *y, bool fuse_dot) {
-  const int lpr = c->spmv_lpr;
-  const int grid = std::min(cdiv((int64_t)c->n_own * lpr, 256), MAX_PARTIALS);
-#define FEA_SPMV(L)                                                                                        \
-  do {                                                                                                     \
-    if (fuse_dot)                                                                                          \
-      fea::spmv_bsr_kernel<L, true><<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, x, y, \
-                                                                 c->partials, c->counters + 0, c->ctl);    \
-    else                                                                                                   \
-      fea::spmv_bsr_kernel<L, false><<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, x, y, \
-                                                                  c->partials, c->counters + 0, c->ctl);   \
-  } while (0)
-  switch (lpr) {
-    case 4: FEA_SPMV(4); break;
-    case 8: FEA_SPMV(8); break;
-    case 32: FEA_SPMV(32); break;
-    default: FEA_SPMV(16); break;
-  }
-#undef FEA_SPMV
+  const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), MAX_PARTIALS);
+  if (fuse_dot)
+    fea::spmv_sell_kernel<true><<<grid, 256, 0, c->stream>>>(c->plan.n_slices, c->slice_ptr, c->sell_row, c->bcol,
+                                                             c->vals, x, y, c->partials, c->counters + 0, c->ctl);
+  else
+    fea::spmv_sell_kernel<false><<<grid, 256, 0, c->stream>>>(c->plan.n_slices, c->slice_ptr, c->sell_row, c->bcol,
+                                                              c->vals, x, y, c->partials, c->counters + 0, c->ctl);
   LAUNCHED();
   return FEA_GPU_OK;
 }
@@ -655,10 +653,10 @@ extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
     fea::axpy_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, -1.0, c->q, c->R);
     LAUNCHED();
   }
-  const int grid = std::min(cdiv((int64_t)c->n_own * 32, 256), 148 * 16);
-  fea::cancel_kernel<<<grid, 256, 0, c->stream>>>(c->n_own, c->browptr, c->bcol, c->vals, c->pflag);
+  const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), 148 * 32);
+  fea::cancel_kernel<<<grid, 256, 0, c->stream>>>(sell_mat(c), c->pflag);
   LAUNCHED();
-  fea::rhs_fix_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->diag, c->pflag, c->pval, lambda, c->R);
+  fea::rhs_fix_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->pflag, c->pval, lambda, c->R);
   LAUNCHED();
   phase_end(c, PH_BC);
   return FEA_GPU_OK;
@@ -666,8 +664,8 @@ extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
 
 extern "C" int fea_gpu_save_stiffness(fea_gpu_handle c) {
   CHECK_H(c);
-  if (!c->vals_saved) TRY(dev_alloc(&c->vals_saved, (size_t)c->nnzb * 9));
-  CU(cudaMemcpyAsync(c->vals_saved, c->vals, sizeof(double) * (size_t)c->nnzb * 9, cudaMemcpyDeviceToDevice, c->stream));
+  if (!c->vals_saved) TRY(dev_alloc(&c->vals_saved, (size_t)c->n_slots * 9));
+  CU(cudaMemcpyAsync(c->vals_saved, c->vals, sizeof(double) * (size_t)c->n_slots * 9, cudaMemcpyDeviceToDevice, c->stream));
   return FEA_GPU_OK;
 }
 extern "C" int fea_gpu_restore_stiffness(fea_gpu_handle c) {
@@ -676,7 +674,7 @@ extern "C" int fea_gpu_restore_stiffness(fea_gpu_handle c) {
     g_err = "no saved stiffness";
     return FEA_GPU_ERR_ARG;
   }
-  CU(cudaMemcpyAsync(c->vals, c->vals_saved, sizeof(double) * (size_t)c->nnzb * 9, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->vals, c->vals_saved, sizeof(double) * (size_t)c->n_slots * 9, cudaMemcpyDeviceToDevice, c->stream));
   return FEA_GPU_OK;
 }
 
@@ -691,7 +689,7 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
   phase_begin(c, PH_PCG);
   c->sp_used = 0;
 
-  fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->diag, c->dinv);
+  fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->dinv);
   LAUNCHED();
   {
     // PCG's ||r|| is not monotone and plateaus grow with the mesh: scale the window
@@ -825,30 +823,39 @@ extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, 
   const fea::Plan &pl = c->plan;
   if (n_rows) *n_rows = 3 * (int64_t)c->n_own;
   if (nnz) *nnz = 9 * c->nnzb;
+  // rows are returned in ascending GLOBAL id (the device keeps them in Morton / SELL order)
+  std::vector<int32_t> by_gid((size_t)c->n_own);
+  for (int32_t l = 0; l < c->n_own; ++l) by_gid[(size_t)l] = l;
+  std::sort(by_gid.begin(), by_gid.end(),
+            [&](int32_t a, int32_t b) { return pl.node_gid[(size_t)a] < pl.node_gid[(size_t)b]; });
   if (rows)
-    for (int32_t l = 0; l < c->n_own; ++l)
-      for (int i = 0; i < 3; ++i) rows[3 * (size_t)l + i] = 3 * pl.node_gid[(size_t)l] + i;
+    for (int32_t k = 0; k < c->n_own; ++k)
+      for (int i = 0; i < 3; ++i) rows[3 * (size_t)k + i] = 3 * pl.node_gid[(size_t)by_gid[(size_t)k]] + i;
   if (!rowptr && !colidx && !vals) return FEA_GPU_OK;
-  std::vector<double> bv;
+  std::vector<double> sv;
   if (vals) {
-    bv.resize(9 * (size_t)c->nnzb);
-    CU(cudaMemcpyAsync(bv.data(), c->vals, sizeof(double) * bv.size(), cudaMemcpyDeviceToHost, c->stream));
+    sv.resize(9 * (size_t)c->n_slots);
+    CU(cudaMemcpyAsync(sv.data(), c->vals, sizeof(double) * sv.size(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   // columns are ascending in LOCAL ids; re-sort each block row by GLOBAL id for the export
   std::vector<std::pair<int32_t, int32_t>> order;
   int64_t out = 0;
-  for (int32_t l = 0; l < c->n_own; ++l) {
+  for (int32_t k = 0; k < c->n_own; ++k) {
+    const int32_t l = by_gid[(size_t)k];
     const int32_t b0 = pl.browptr[(size_t)l], b1 = pl.browptr[(size_t)l + 1];
+    const int32_t rl = pl.row_lane[(size_t)l];
+    const int64_t sbase = pl.slice_ptr[(size_t)(rl / fea::SELL_C)];
+    const int lane = rl % fea::SELL_C;
     order.clear();
-    for (int32_t k = b0; k < b1; ++k) order.emplace_back(pl.node_gid[(size_t)pl.bcol[(size_t)k]], k);
+    for (int32_t q = b0; q < b1; ++q) order.emplace_back(pl.node_gid[(size_t)pl.bcol[(size_t)q]], q - b0);
     std::sort(order.begin(), order.end());
     for (int i = 0; i < 3; ++i) {
-      if (rowptr) rowptr[3 * (size_t)l + i] = (int32_t)out;
+      if (rowptr) rowptr[3 * (size_t)k + i] = (int32_t)out;
       for (auto &pr : order)
         for (int j = 0; j < 3; ++j, ++out) {
           if (colidx) colidx[out] = 3 * pr.first + j;
-          if (vals) vals[out] = bv[9 * (size_t)pr.second + 3 * i + j];
+          if (vals) vals[out] = sv[(size_t)(9 * (sbase + (int64_t)pr.second * fea::SELL_C) + 32 * (3 * i + j) + lane)];
         }
     }
   }
@@ -959,8 +966,7 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   if (!c || !name) return FEA_GPU_ERR_ARG;
   const std::string k(name);
   const int v = (int)value;
-  if (k == "spmv_lpr" && (v == 4 || v == 8 || v == 16 || v == 32)) c->spmv_lpr = v;
-  else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
+  if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else {
     g_err = "unknown parameter or value out of range: " + k;

@@ -21,26 +21,78 @@
 
 namespace fea {
 
-static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nranks) {
-  p.owner.assign((size_t)n_nodes, 0);
-  if (nranks <= 1) return;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+// 63-bit Morton key of a point on a 2^21 grid (uniform scale so cells are cubes)
+static inline uint64_t spread21(uint64_t v) {
+  v &= 0x1fffffULL;
+  v = (v | (v << 32)) & 0x1f00000000ffffULL;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffULL;
+  v = (v | (v << 8)) & 0x100f00f00f00f00fULL;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ULL;
+  v = (v | (v << 2)) & 0x1249249249249249ULL;
+  return v;
+}
+
+struct MortonBox {
+  double lo[3], inv;
+  uint64_t key(const double *x) const {
+    uint64_t q[3];
+    for (int d = 0; d < 3; ++d) {
+      double t = (x[d] - lo[d]) * inv;
+      t = t < 0 ? 0 : (t > 2097151.0 ? 2097151.0 : t);
+      q[d] = (uint64_t)t;
+    }
+    return spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+  }
+};
+
+static MortonBox bounding_box(int32_t n_nodes, const double *X0, double (&hi)[3]) {
+  MortonBox b;
+  for (int d = 0; d < 3; ++d) { b.lo[d] = 1e300; hi[d] = -1e300; }
   for (int32_t i = 0; i < n_nodes; ++i)
     for (int d = 0; d < 3; ++d) {
-      lo[d] = std::min(lo[d], X0[3 * (size_t)i + d]);
+      b.lo[d] = std::min(b.lo[d], X0[3 * (size_t)i + d]);
       hi[d] = std::max(hi[d], X0[3 * (size_t)i + d]);
     }
-  int axis = 0;
-  for (int d = 1; d < 3; ++d)
-    if (hi[d] - lo[d] > hi[axis] - lo[axis]) axis = d;
+  double ext = 0;
+  for (int d = 0; d < 3; ++d) ext = std::max(ext, hi[d] - b.lo[d]);
+  b.inv = ext > 0 ? 2097151.0 / ext : 0.0;
+  return b;
+}
+
+// owner[] by equal-count chunks along the longest axis; pos_in_owner[] = Morton rank of the
+// node among its owner's nodes (every rank computes the same two arrays from the global mesh)
+static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nranks, const MortonBox &box,
+                            const double (&hi)[3]) {
+  p.owner.assign((size_t)n_nodes, 0);
   std::vector<int32_t> order((size_t)n_nodes);
   std::iota(order.begin(), order.end(), 0);
+  if (nranks > 1) {
+    int axis = 0;
+    for (int d = 1; d < 3; ++d)
+      if (hi[d] - box.lo[d] > hi[axis] - box.lo[axis]) axis = d;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      double xa = X0[3 * (size_t)a + axis], xb = X0[3 * (size_t)b + axis];
+      return xa < xb || (xa == xb && a < b);
+    });
+    for (int64_t k = 0; k < n_nodes; ++k)
+      p.owner[(size_t)order[(size_t)k]] = (int32_t)(k * nranks / n_nodes);
+  }
+  std::vector<uint64_t> key((size_t)n_nodes);
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < n_nodes; ++i) key[(size_t)i] = box.key(X0 + 3 * (size_t)i);
+  std::iota(order.begin(), order.end(), 0);
   std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-    double xa = X0[3 * (size_t)a + axis], xb = X0[3 * (size_t)b + axis];
-    return xa < xb || (xa == xb && a < b);
+    if (p.owner[(size_t)a] != p.owner[(size_t)b]) return p.owner[(size_t)a] < p.owner[(size_t)b];
+    if (key[(size_t)a] != key[(size_t)b]) return key[(size_t)a] < key[(size_t)b];
+    return a < b;
   });
-  for (int64_t k = 0; k < n_nodes; ++k)
-    p.owner[(size_t)order[(size_t)k]] = (int32_t)(k * nranks / n_nodes);
+  p.pos_in_owner.assign((size_t)n_nodes, 0);
+  int32_t run = 0;
+  for (int64_t k = 0; k < n_nodes; ++k) {
+    const int32_t g = order[(size_t)k];
+    if (k > 0 && p.owner[(size_t)g] != p.owner[(size_t)order[(size_t)k - 1]]) run = 0;
+    p.pos_in_owner[(size_t)g] = run++;
+  }
 }
 
 void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
@@ -53,8 +105,11 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
   p.nranks = nranks;
   p.n_nodes_global = n_nodes;
   p.n_elems_global = n_elems;
-  partition_nodes(p, n_nodes, X0, nranks);
+  double box_hi[3];
+  const MortonBox box = bounding_box(n_nodes, X0, box_hi);
+  partition_nodes(p, n_nodes, X0, nranks, box, box_hi);
   const std::vector<int32_t> &owner = p.owner;
+  const std::vector<int32_t> &pos = p.pos_in_owner;
 
   // ---- local elements, local node numbering ---------------------------------
   std::vector<uint8_t> used((size_t)n_nodes, 0);
@@ -67,6 +122,19 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     p.elem_gid.push_back(e);
     for (int a = 0; a < NEN; ++a) used[(size_t)c[a]] = 1;
   }
+  {
+    std::vector<std::pair<uint64_t, int32_t>> ek(p.elem_gid.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)ek.size(); ++k) {
+      const int32_t *c = conn + (size_t)p.elem_gid[(size_t)k] * NEN;
+      double cen[3] = {0, 0, 0};
+      for (int a = 0; a < 4; ++a)
+        for (int d = 0; d < 3; ++d) cen[d] += 0.25 * X0[3 * (size_t)c[a] + d];
+      ek[(size_t)k] = {box.key(cen), p.elem_gid[(size_t)k]};
+    }
+    std::sort(ek.begin(), ek.end());
+    for (size_t k = 0; k < ek.size(); ++k) p.elem_gid[k] = ek[k].second;
+  }
   p.n_elems = (int32_t)p.elem_gid.size();
   if ((int64_t)p.n_elems * NTRI >= (int64_t)0x7fffffff)
     throw std::runtime_error("too many local elements for 31-bit gather indices");
@@ -76,11 +144,14 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     if (owner[(size_t)i] == rank) p.node_gid.push_back(i);
   p.n_own = (int32_t)p.node_gid.size();
   {
+    std::vector<int32_t> mine(p.node_gid);
+    for (int32_t g : mine) p.node_gid[(size_t)pos[(size_t)g]] = g;   // owned: by Morton rank
     std::vector<int32_t> ghosts;
     for (int32_t i = 0; i < n_nodes; ++i)
       if (used[(size_t)i] && owner[(size_t)i] != rank) ghosts.push_back(i);
     std::sort(ghosts.begin(), ghosts.end(), [&](int32_t a, int32_t b) {
-      return owner[(size_t)a] < owner[(size_t)b] || (owner[(size_t)a] == owner[(size_t)b] && a < b);
+      return owner[(size_t)a] < owner[(size_t)b] ||
+             (owner[(size_t)a] == owner[(size_t)b] && pos[(size_t)a] < pos[(size_t)b]);
     });
     p.node_gid.insert(p.node_gid.end(), ghosts.begin(), ghosts.end());
   }
@@ -108,7 +179,11 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
   p.rsrc.resize((size_t)p.rptr[(size_t)n_own]);
   {
     std::vector<int32_t> cur(p.rptr.begin(), p.rptr.end() - 1);
-    for (int32_t le = 0; le < p.n_elems; ++le)      // ascending element order
+    std::vector<int32_t> by_gid((size_t)p.n_elems);
+    std::iota(by_gid.begin(), by_gid.end(), 0);
+    std::sort(by_gid.begin(), by_gid.end(),
+              [&](int32_t a, int32_t b) { return p.elem_gid[(size_t)a] < p.elem_gid[(size_t)b]; });
+    for (int32_t le : by_gid)      // ascending GLOBAL element id: the reference's accumulation order
       for (int a = 0; a < NEN; ++a) {
         int32_t l = p.conn[(size_t)le * NEN + a];
         if (l < n_own) p.rsrc[(size_t)cur[(size_t)l]++] = le * NEN + a;
@@ -195,6 +270,75 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     }
   }
 
+  // ---- SELL-32-sigma layout of the same pattern -----------------------------------
+  {
+    std::vector<int32_t> perm((size_t)n_own);
+    std::iota(perm.begin(), perm.end(), 0);
+    for (int32_t w0 = 0; w0 < n_own; w0 += SELL_SIGMA) {
+      const int32_t w1 = std::min(n_own, w0 + SELL_SIGMA);
+      std::stable_sort(perm.begin() + w0, perm.begin() + w1,
+                       [&](int32_t a, int32_t b) { return rowlen[(size_t)a] > rowlen[(size_t)b]; });
+    }
+    p.n_slices = (n_own + SELL_C - 1) / SELL_C;
+    p.sell_row.assign((size_t)p.n_slices * SELL_C, -1);
+    p.row_lane.assign((size_t)n_own, 0);
+    p.slice_ptr.assign((size_t)p.n_slices + 1, 0);
+    int64_t slots = 0;
+    for (int32_t s = 0; s < p.n_slices; ++s) {
+      int32_t width = 0;
+      for (int l = 0; l < SELL_C; ++l) {
+        const int64_t k = (int64_t)s * SELL_C + l;
+        if (k >= n_own) break;
+        const int32_t r = perm[(size_t)k];
+        p.sell_row[(size_t)k] = r;
+        p.row_lane[(size_t)r] = (int32_t)k;
+        width = std::max(width, rowlen[(size_t)r]);
+      }
+      slots += (int64_t)width * SELL_C;
+      if (slots * 9 >= (int64_t)0x7fffffff) throw std::runtime_error("local SELL matrix exceeds 2^31 values");
+      p.slice_ptr[(size_t)s + 1] = (int32_t)slots;
+    }
+    p.sbcol.assign((size_t)slots, 0);
+    p.scptr.assign((size_t)slots + 1, 0);
+    p.sdiag.assign((size_t)n_own, 0);
+    // slot of (row r, j-th block)
+    auto slot_of = [&](int32_t r, int32_t j) {
+      const int32_t k = p.row_lane[(size_t)r];
+      return p.slice_ptr[(size_t)(k / SELL_C)] + j * SELL_C + (k % SELL_C);
+    };
+#pragma omp parallel for schedule(static)
+    for (int32_t s = 0; s < p.n_slices; ++s) {
+      const int32_t width = (p.slice_ptr[(size_t)s + 1] - p.slice_ptr[(size_t)s]) / SELL_C;
+      for (int l = 0; l < SELL_C; ++l) {
+        const int32_t r = p.sell_row[(size_t)s * SELL_C + l];
+        const int32_t len = r >= 0 ? rowlen[(size_t)r] : 0;
+        for (int32_t j = 0; j < width; ++j) {
+          const int32_t slot = p.slice_ptr[(size_t)s] + j * SELL_C + l;
+          if (j < len) {
+            const int32_t pcsr = p.browptr[(size_t)r] + j;
+            p.sbcol[(size_t)slot] = p.bcol[(size_t)pcsr];
+            p.scptr[(size_t)slot + 1] = p.cptr[(size_t)pcsr + 1] - p.cptr[(size_t)pcsr];
+          } else {
+            p.sbcol[(size_t)slot] = r >= 0 ? r : 0;   // padding: zero value times a finite x
+          }
+        }
+        if (r >= 0) {
+          const int32_t jd = p.diag[(size_t)r] - p.browptr[(size_t)r];
+          p.sdiag[(size_t)r] = 9 * (p.slice_ptr[(size_t)s] + jd * SELL_C) + l;
+        }
+      }
+    }
+    for (int64_t k = 0; k < slots; ++k) p.scptr[(size_t)k + 1] += p.scptr[(size_t)k];
+    p.scsrc.resize(p.csrc.size());
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int32_t r = 0; r < n_own; ++r)
+      for (int32_t j = 0; j < rowlen[(size_t)r]; ++j) {
+        const int32_t pcsr = p.browptr[(size_t)r] + j, slot = slot_of(r, j);
+        std::copy(p.csrc.begin() + p.cptr[(size_t)pcsr], p.csrc.begin() + p.cptr[(size_t)pcsr + 1],
+                  p.scsrc.begin() + p.scptr[(size_t)slot]);
+      }
+  }
+
   // ---- halo lists ---------------------------------------------------------------
   p.nbr_rank.clear();
   p.send_ptr.assign(1, 0);
@@ -221,7 +365,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     int32_t ghost_pos = 0;
     for (int q = 0; q < nranks; ++q) {
       std::vector<int32_t> &s = send[(size_t)q];
-      std::sort(s.begin(), s.end());
+      std::sort(s.begin(), s.end(), [&](int32_t a, int32_t b) { return pos[(size_t)a] < pos[(size_t)b]; });
       s.erase(std::unique(s.begin(), s.end()), s.end());
       int32_t nrecv = 0;
       while (p.n_own + ghost_pos + nrecv < p.n_local &&
@@ -282,6 +426,8 @@ void plan_counts(const Plan &pl, int64_t out[16]) {
   out[7] = pl.n_local - pl.n_own;
   out[8] = pl.n_nodes_global;
   out[9] = pl.n_elems_global;
+  out[10] = pl.n_slots();
+  out[11] = pl.n_slices;
 }
 }  // namespace fea
 
@@ -312,6 +458,19 @@ extern "C" int fea_plan_arrays(fea_plan_handle p, int32_t *local_node_gid,
   copy_out(send_ptr, pl.send_ptr);
   copy_out(send_nodes, pl.send_nodes);
   copy_out(recv_ptr, pl.recv_ptr);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_plan_sell_arrays(fea_plan_handle p, int32_t *slice_ptr, int32_t *sell_row, int32_t *sbcol,
+                                    int32_t *scptr, uint32_t *scsrc, int32_t *sdiag) {
+  if (!p) return FEA_GPU_ERR_ARG;
+  const fea::Plan &pl = p->plan;
+  copy_out(slice_ptr, pl.slice_ptr);
+  copy_out(sell_row, pl.sell_row);
+  copy_out(sbcol, pl.sbcol);
+  copy_out(scptr, pl.scptr);
+  copy_out(scsrc, pl.scsrc);
+  copy_out(sdiag, pl.sdiag);
   return FEA_GPU_OK;
 }
 

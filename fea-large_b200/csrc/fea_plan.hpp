@@ -16,17 +16,23 @@ constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
 // index of pair (a<=b) in the packed upper triangle, row-major
 inline int tri_index(int a, int b) { return a * NEN - (a * (a - 1)) / 2 + (b - a); }
 
+constexpr int SELL_C = 32;              // rows per SELL slice = one warp
+constexpr int SELL_SIGMA = 2048;        // rows per length-sorting window
+
 struct Plan {
   int rank = 0, nranks = 1;
   int64_t n_nodes_global = 0, n_elems_global = 0;
 
-  // local numbering: owned nodes (ascending global id) then ghosts (by owner, then id)
+  // local numbering: owned nodes in Morton (Z-curve) order of their reference coordinates,
+  // then ghosts grouped by owner, each group in that owner's own order.  Elements are local
+  // in Morton order of their centroid.  (L2 locality for the gather and the x-gathers.)
   int32_t n_own = 0, n_local = 0, n_elems = 0;
   std::vector<int32_t> node_gid;        // [n_local]
   std::vector<int32_t> elem_gid;        // [n_elems] ascending
   std::vector<int32_t> conn;            // [n_elems][10] local node ids
   std::vector<uint8_t> elem_owned;      // [n_elems] 1 if this rank owns the element (owner of its node 0)
   std::vector<int32_t> owner;           // [n_nodes_global]
+  std::vector<int32_t> pos_in_owner;    // [n_nodes_global] index of the node in its owner's numbering
 
   // block CSR over owned rows
   std::vector<int32_t> browptr;         // [n_own+1]
@@ -35,6 +41,20 @@ struct Plan {
   // stiffness gather map
   std::vector<int32_t> cptr;            // [nnzb+1]
   std::vector<uint32_t> csrc;           // [ncontrib]
+  // SELL-32-sigma copy of the block pattern: what the device kernels use.  Rows are sorted by
+  // length inside windows of SELL_SIGMA rows and cut into slices of 32; slot (row r = lane l of
+  // slice s, j-th block of the row) = slice_ptr[s] + 32 j + l, its 9 values live at
+  // 9 (slice_ptr[s] + 32 j) + 32 c + l  (c = 3 i + j'): every warp load is 256 contiguous bytes.
+  int32_t n_slices = 0;
+  std::vector<int32_t> sell_row;        // [n_slices*32] local row of each lane, -1 = padding lane
+  std::vector<int32_t> row_lane;        // [n_own] slice*32 + lane of each row
+  std::vector<int32_t> slice_ptr;       // [n_slices+1] first slot of each slice
+  std::vector<int32_t> sbcol;           // [n_slots] column node of each slot (padding: the row's own node)
+  std::vector<int32_t> scptr;           // [n_slots+1] gather map in slot order
+  std::vector<uint32_t> scsrc;          // [ncontrib]
+  std::vector<int32_t> sdiag;           // [n_own] value index of the (0,0) entry of the diagonal block
+  int64_t n_slots() const { return (int64_t)sbcol.size(); }
+
   // residual gather map (node -> (element, local node))
   std::vector<int32_t> rptr;            // [n_own+1]
   std::vector<int32_t> rsrc;            // [.] elem*10 + a

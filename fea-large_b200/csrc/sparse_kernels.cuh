@@ -75,37 +75,70 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials /*
 }
 
 // ---------------------------------------------------------------------------------
-// K3: gather assembly.  One warp per block row; lanes stride over the row's flat value
-// range so stores are contiguous.  Each scalar sums its contributions in the order of the
-// precomputed list (element-ascending), so results are bit-reproducible run to run.
-// Optionally applies the Dirichlet cancellation in the same pass.
+// SELL-32 block layout (see fea_plan.hpp): slice s = 32 rows (one per lane) x width_s block
+// columns; slot = slice_ptr[s] + 32 j + lane; value (slot, c) at 9 (slice_ptr[s] + 32 j) + 32 c + lane.
+// One warp walks one slice; every load and store below is 256 contiguous bytes per warp.
 
+struct SellMat {
+  int n_slices;
+  const int32_t *slice_ptr;   // [n_slices + 1]
+  const int32_t *sell_row;    // [n_slices * 32], -1 = padding lane
+  const int32_t *bcol;        // [n_slots] column node
+  double *vals;               // [n_slots * 9]
+};
+
+// K3: gather assembly.  Each lane owns one block slot and sums its contributions in the order
+// of the precomputed list (ascending global element id = the reference's element-major
+// accumulation, fea_solver.c:878-882), so results are bit-reproducible run to run and need
+// no atomics.  Optionally applies the Dirichlet cancellation in the same pass.
 __global__ void __launch_bounds__(256)
-gather_blocks_kernel(int n_rows, const int32_t *__restrict__ browptr,
-                     const int32_t *__restrict__ bcol, const int32_t *__restrict__ cptr,
-                     const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
-                     double *__restrict__ vals, const uint8_t *__restrict__ pflag /* may be null */) {
+gather_blocks_kernel(SellMat A, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
+                     const double *__restrict__ Ke, const uint8_t *__restrict__ pflag /* may be null */) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps_per_grid) {
-    const int f0 = browptr[row] * 9, f1 = browptr[row + 1] * 9;  // plan guarantees < 2^31
-    for (int f = f0 + lane; f < f1; f += 32) {
-      const int p = f / 9;
-      const int c = f - p * 9;
-      const int ct = (c % 3) * 3 + c / 3;
-      const int k0 = cptr[p], k1 = cptr[p + 1];
-      double acc = 0.0;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < A.n_slices; s += warps_per_grid) {
+    const int base = A.slice_ptr[s];
+    const int width = (A.slice_ptr[s + 1] - base) >> 5;
+    const int row = A.sell_row[s * 32 + lane];
+    uint8_t rf0 = 0, rf1 = 0, rf2 = 0;
+    if (pflag && row >= 0) {
+      rf0 = pflag[3 * (size_t)row];
+      rf1 = pflag[3 * (size_t)row + 1];
+      rf2 = pflag[3 * (size_t)row + 2];
+    }
+    for (int j = 0; j < width; ++j) {
+      const int slot = base + (j << 5) + lane;
+      const int k0 = cptr[slot], k1 = cptr[slot + 1];
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int k = k0; k < k1; ++k) {
-        const uint32_t s = csrc[k];
-        acc += Ke[(size_t)(s & 0x7fffffffu) * 9 + ((s >> 31) ? ct : c)];
+        const uint32_t src = csrc[k];
+        const double *b = Ke + (size_t)(src & 0x7fffffffu) * 9;
+        double v[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) v[c] = b[c];
+        if (src >> 31) {  // stored block is K_e[b][a]: add its transpose
+#pragma unroll
+          for (int c = 0; c < 9; ++c) acc[c] += v[(c % 3) * 3 + c / 3];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 9; ++c) acc[c] += v[c];
+        }
       }
       if (pflag) {
-        const int i = c / 3, j = c - 3 * i;
-        const int colnode = bcol[p];
-        const bool diag = (colnode == row) && (i == j);
-        if (!diag && (pflag[3 * (size_t)row + i] | pflag[3 * (size_t)colnode + j])) acc = 0.0;
+        const int col = A.bcol[slot];
+        const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
+        const bool dg = (col == row);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const int i = c / 3, jj = c % 3;
+          const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
+          const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
+          if ((rf | cf) && !(dg && i == jj)) acc[c] = 0.0;
+        }
       }
-      vals[f] = acc;
+      double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) out[c * 32] = acc[c];
     }
   }
 }
@@ -131,48 +164,58 @@ gather_residual_kernel(int n_rows, const int32_t *__restrict__ rptr, const int32
 // K4: zero rows and columns of prescribed DOFs keeping the diagonal (sp_matrix_cross_cancellation
 // as used at fea_solver.c:1255); RHS rows become diag * presc (:1256)
 __global__ void __launch_bounds__(256)
-cancel_kernel(int n_rows, const int32_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
-              double *__restrict__ vals, const uint8_t *__restrict__ pflag) {
+cancel_kernel(SellMat A, const uint8_t *__restrict__ pflag) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps_per_grid) {
-    const int f0 = browptr[row] * 9, f1 = browptr[row + 1] * 9;
-    const uint8_t r0 = pflag[3 * (size_t)row], r1 = pflag[3 * (size_t)row + 1], r2 = pflag[3 * (size_t)row + 2];
-    for (int f = f0 + lane; f < f1; f += 32) {
-      const int p = f / 9;
-      const int c = f - p * 9;
-      const int i = c / 3, j = c - 3 * i;
-      const int colnode = bcol[p];
-      const uint8_t rf = i == 0 ? r0 : (i == 1 ? r1 : r2);
-      if ((rf | pflag[3 * (size_t)colnode + j]) && !((colnode == row) && (i == j))) vals[f] = 0.0;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < A.n_slices; s += warps_per_grid) {
+    const int base = A.slice_ptr[s];
+    const int width = (A.slice_ptr[s + 1] - base) >> 5;
+    const int row = A.sell_row[s * 32 + lane];
+    if (row < 0) continue;
+    const uint8_t rf0 = pflag[3 * (size_t)row], rf1 = pflag[3 * (size_t)row + 1], rf2 = pflag[3 * (size_t)row + 2];
+    for (int j = 0; j < width; ++j) {
+      const int slot = base + (j << 5) + lane;
+      const int col = A.bcol[slot];
+      const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
+      if (!(rf0 | rf1 | rf2 | cf0 | cf1 | cf2)) continue;
+      const bool dg = (col == row);
+      double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const int i = c / 3, jj = c % 3;
+        const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
+        const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
+        if ((rf | cf) && !(dg && i == jj)) out[c * 32] = 0.0;
+      }
     }
   }
 }
 
-__global__ void rhs_fix_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ diag,
+// sdiag[row] = value index of the (0,0) entry of the row's diagonal block; (i,i) is 4 i * 32 further
+__global__ void rhs_fix_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ sdiag,
                                const uint8_t *__restrict__ pflag, const double *__restrict__ pval,
                                double lambda, double *__restrict__ R) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   if (pflag[t]) {
     const int row = t / 3, i = t - 3 * row;
-    R[t] = vals[(size_t)diag[row] * 9 + 4 * i] * (pval[t] * lambda);
+    R[t] = vals[(size_t)sdiag[row] + 128 * i] * (pval[t] * lambda);
   }
 }
 
-__global__ void jacobi_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ diag,
+__global__ void jacobi_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ sdiag,
                               double *__restrict__ dinv) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int row = t / 3, i = t - 3 * row;
-  const double d = vals[(size_t)diag[row] * 9 + 4 * i];
+  const double d = vals[(size_t)sdiag[row] + 128 * i];
   dinv[t] = d != 0.0 ? 1.0 / d : 1.0;
 }
 
 // ---------------------------------------------------------------------------------
-// K5: y = A x for 3x3-block CSR.  LPR lanes cooperate on one block row; their loads walk
-// the row's value array contiguously (9 doubles per block, blocks back to back), x is
-// gathered through L1/L2.  Optionally fuses the partial of x_row . y_row (p.Ap of CG).
+// K5: y = A x, 3x3 blocks in SELL-32.  Lane = row, no shuffles, no index arithmetic beyond
+// the slot stride; x is gathered through L1/L2 (24 contiguous bytes per block).  Optionally
+// fuses the partial of x_row . y_row (p.Ap of CG).
 
 struct PcgCtl {
   double pq;        // p . A p (global)
@@ -189,40 +232,35 @@ struct PcgCtl {
   int stall_limit;
 };
 
-template <int LPR, bool FUSE_DOT>
+template <bool FUSE_DOT>
 __global__ void __launch_bounds__(256)
-spmv_bsr_kernel(int n_rows, const int32_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
-                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                double *partials, unsigned int *counter, PcgCtl *ctl) {
+spmv_sell_kernel(int n_slices, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ sell_row,
+                 const int32_t *__restrict__ bcol, const double *__restrict__ vals,
+                 const double *__restrict__ x, double *__restrict__ y, double *partials,
+                 unsigned int *counter, PcgCtl *ctl) {
   __shared__ double red[32];
   if (FUSE_DOT && ctl->done) return;
-  const int sub = threadIdx.x % LPR;
-  constexpr int GROUPS = 256 / LPR;  // block rows handled per CTA per sweep
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
-  // the sweep bound depends on blockIdx only, so every lane of a warp reaches the shuffles
-  for (int base = blockIdx.x * GROUPS; base < n_rows; base += gridDim.x * GROUPS) {
-    const int row = base + threadIdx.x / LPR;
-    const bool valid = row < n_rows;
-    const int b0 = valid ? browptr[row] : 0, b1 = valid ? browptr[row + 1] : 0;
-    const int64_t f0 = (int64_t)b0 * 9;
-    const int nf = (b1 - b0) * 9;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps_per_grid) {
+    const int base = slice_ptr[s];
+    const int width = (slice_ptr[s + 1] - base) >> 5;
+    const int row = sell_row[s * 32 + lane];
+    const double *v = vals + (size_t)base * 9 + lane;
+    const int32_t *bc = bcol + base + lane;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int f = sub; f < nf; f += LPR) {
-      const int blk = f / 9;
-      const int c = f - blk * 9;
-      const int i = c / 3, j = c - 3 * i;
-      const double v = vals[f0 + f] * x[3 * (size_t)bcol[b0 + blk] + j];
-      a0 += (i == 0) ? v : 0.0;
-      a1 += (i == 1) ? v : 0.0;
-      a2 += (i == 2) ? v : 0.0;
+#pragma unroll 2
+    for (int j = 0; j < width; ++j) {
+      const int col = bc[j << 5];
+      const double *xc = x + 3 * (size_t)col;
+      const double x0 = xc[0], x1 = xc[1], x2 = xc[2];
+      const double *vj = v + (size_t)j * 288;
+      a0 = fma(vj[0], x0, fma(vj[32], x1, fma(vj[64], x2, a0)));
+      a1 = fma(vj[96], x0, fma(vj[128], x1, fma(vj[160], x2, a1)));
+      a2 = fma(vj[192], x0, fma(vj[224], x1, fma(vj[256], x2, a2)));
     }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-      a0 += __shfl_down_sync(0xffffffffu, a0, o, LPR);
-      a1 += __shfl_down_sync(0xffffffffu, a1, o, LPR);
-      a2 += __shfl_down_sync(0xffffffffu, a2, o, LPR);
-    }
-    if (valid && sub == 0) {
+    if (row >= 0) {
       y[3 * (size_t)row] = a0;
       y[3 * (size_t)row + 1] = a1;
       y[3 * (size_t)row + 2] = a2;
@@ -231,8 +269,8 @@ spmv_bsr_kernel(int n_rows, const int32_t *__restrict__ browptr, const int32_t *
     }
   }
   if (FUSE_DOT) {
-    double v[1] = {dot};
-    if (grid_reduce<1>(v, partials, counter, red)) ctl->pq = v[0];
+    double t[1] = {dot};
+    if (grid_reduce<1>(t, partials, counter, red)) ctl->pq = t[0];
   }
 }
 

@@ -34,7 +34,7 @@ SYMBOLS = [
     "fea_gpu_counts", "fea_gpu_launch_count", "fea_gpu_timer_start", "fea_gpu_timer_stop",
     "fea_gpu_sync", "fea_gpu_phase_ms", "fea_gpu_bench_spmv", "fea_gpu_measure_peaks",
     "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
-    "fea_plan_node_owner", "fea_mesh_block",
+    "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_mesh_block",
 ]
 
 _lib = None
@@ -141,6 +141,17 @@ class Plan:
         self.owner = np.empty(self.n_nodes, np.int32)
         lib().fea_plan_node_owner.argtypes = [C.c_void_p, _ip]
         _check(lib().fea_plan_node_owner(self.h, self.owner))
+        self.n_slots, self.n_slices = int(cnt[10]), int(cnt[11])
+        self.slice_ptr = np.empty(self.n_slices + 1, np.int32)
+        self.sell_row = np.empty(32 * self.n_slices, np.int32)
+        self.sbcol = np.empty(self.n_slots, np.int32)
+        self.scptr = np.empty(self.n_slots + 1, np.int32)
+        self.scsrc = np.empty(self.n_contrib, np.uint32)
+        self.sdiag = np.empty(self.n_own, np.int32)
+        f = lib().fea_plan_sell_arrays
+        f.argtypes = [C.c_void_p] * 7
+        _check(f(self.h, *[a.ctypes.data for a in (self.slice_ptr, self.sell_row, self.sbcol, self.scptr,
+                                                    self.scsrc, self.sdiag)]))
 
     def close(self):
         if self.h:
@@ -293,7 +304,7 @@ class FeaGpu:
         lib().fea_gpu_counts.argtypes = [C.c_void_p, _lp]
         _check(lib().fea_gpu_counts(self.h, out))
         keys = ["owned_nodes", "local_nodes", "local_elems", "nnzb", "contribs", "neighbours",
-                "halo_sent", "halo_recv", "global_nodes", "global_elems"]
+                "halo_sent", "halo_recv", "global_nodes", "global_elems", "sell_slots", "sell_slices"]
         return dict(zip(keys, (int(v) for v in out)))
 
     def phase_ms(self):

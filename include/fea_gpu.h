@@ -154,7 +154,8 @@ int fea_gpu_step_from_host(fea_gpu_handle h, const double *x, int32_t with_stiff
 
 /* out[0]=owned nodes, [1]=local nodes (owned+ghost), [2]=local elements,
  * [3]=block nonzeros (3x3), [4]=gather contributions, [5]=neighbour ranks,
- * [6]=halo nodes sent, [7]=halo nodes received, [8]=global nodes, [9]=global elements */
+ * [6]=halo nodes sent, [7]=halo nodes received, [8]=global nodes, [9]=global elements,
+ * [10]=SELL block slots (incl. padding), [11]=SELL slices */
 int fea_gpu_counts(fea_gpu_handle h, int64_t out[16]);
 /* kernels launched by this library in this process (all handles) */
 int64_t fea_gpu_launch_count(void);
@@ -170,7 +171,7 @@ int fea_gpu_phase_ms(fea_gpu_handle h, double out[16]);
 int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);
 /* measured machine peaks on this device: FP64 FMA TFLOP/s, copy GB/s (read+write) */
 int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs);
-/* tuning knobs: "spmv_lpr" (lanes per block row: 4, 8, 16, 32), "pcg_batch" (iterations
+/* tuning knobs: "pcg_batch" (iterations
  * queued between host convergence checks), "pcg_stall" (iterations without a new best
  * ||r|| before PCG declares the rounding floor; 0 = automatic, max(200, 10 n^(1/3))) */
 int fea_gpu_set_param(fea_gpu_handle h, const char *name, double value);
@@ -186,11 +187,11 @@ int fea_plan_destroy(fea_plan_handle p);
 /* same slots as fea_gpu_counts */
 int fea_plan_counts(fea_plan_handle p, int64_t out[16]);
 /* any pointer may be NULL.
- *   local_node_gid  [local nodes]      global id of each local node (owned first)
- *   local_elem_gid  [local elements]
+ *   local_node_gid  [local nodes]      global id of each local node (owned first, Morton order)
+ *   local_elem_gid  [local elements]   (Morton order of the centroids)
  *   browptr         [owned nodes + 1]  block-row pointers
  *   bcol            [nnzb]             local column node ids, ascending
- *   cptr            [nnzb + 1], csrc [contributions]  gather map (element-ascending);
+ *   cptr            [nnzb + 1], csrc [contributions]  gather map (ascending global element id);
  *                   csrc = elem*55 + tri(a,b) | (1<<31 if the stored block is transposed)
  *   nbr_rank [nbr], send_ptr [nbr+1], send_nodes [sent] (local ids), recv_ptr [nbr+1]
  *                   (ghost offset ranges, in local numbering minus owned count) */
@@ -199,6 +200,11 @@ int fea_plan_arrays(fea_plan_handle p, int32_t *local_node_gid, int32_t *local_e
                     int32_t *nbr_rank, int32_t *send_ptr, int32_t *send_nodes,
                     int32_t *recv_ptr);
 int fea_plan_node_owner(fea_plan_handle p, int32_t *owner /* [n_nodes] */);
+/* the SELL-32 device layout of the same pattern (any pointer may be NULL):
+ *   slice_ptr [slices + 1], sell_row [32 * slices] (-1 = padding lane), sbcol [slots],
+ *   scptr [slots + 1], scsrc [contributions], sdiag [owned nodes] */
+int fea_plan_sell_arrays(fea_plan_handle p, int32_t *slice_ptr, int32_t *sell_row, int32_t *sbcol,
+                         int32_t *scptr, uint32_t *scsrc, int32_t *sdiag);
 
 /* Kuhn (Freudenthal) 6-tet block, 10-node tets in the reference node order:
  * nx*ny*nz cubes on [0,lx]x[y0,y0+ly]x[0,lz]; nodes (2nx+1)(2ny+1)(2nz+1), tets 6*nx*ny*nz.

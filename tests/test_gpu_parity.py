@@ -183,7 +183,10 @@ def test_uniaxial_exact_solution(name, closed):
     """exact-solutions/uniaxial: full Newton at a tight tolerance lands on the closed form."""
     m, _ = load_golden(name)
     g = make_gpu(m)
-    newton_gpu(g, 1, 1e-22, False, 60)
+    # <R,u> falls quadratically (1e-2, 1e-5, 1e-11, 1e-23); stop there rather than keep solving
+    # rounding-noise systems on this BC set, whose K is singular (free rotation about y)
+    us, tols = newton_gpu(g, 1, 1e-18, False, 20)
+    assert len(tols) <= 8
     F, S = g.get_state()
     k1 = 1 + 0.05 / 6
     k2, sig = closed(k1)

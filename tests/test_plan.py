@@ -48,18 +48,56 @@ def test_pattern_and_gather_map_reproduce_oracle_matrix():
     rp, ci, v = o.get_csr()
     p = fg.Plan(m.nodes, m.conn)
     assert p.nnzb * 9 == len(v) == 145737
-    for I in range(p.n_own):   # full 3x3 blocks, ascending columns, identical node sets
-        assert np.array_equal(p.node_gid[p.bcol[p.browptr[I]:p.browptr[I + 1]]], ci[rp[3 * I]:rp[3 * I + 1]][::3] // 3)
-    vals = gather_numpy(p, staged_blocks(o, len(m.conn)))
+    assert sorted(p.node_gid) == list(range(len(m.nodes)))          # a permutation (Morton order)
+    for I in range(p.n_own):   # full 3x3 blocks, identical node sets per row, ascending local columns
+        g = p.node_gid[I]
+        cols = p.bcol[p.browptr[I]:p.browptr[I + 1]]
+        assert np.all(np.diff(cols) > 0)
+        assert np.array_equal(np.sort(p.node_gid[cols]), ci[rp[3 * g]:rp[3 * g + 1]][::3] // 3)
+    vals = gather_numpy(p, staged_blocks(o, len(m.conn))[p.elem_gid])   # csrc indexes LOCAL elements
     A = bsr_to_dense_rows(p, vals, m.n_dof)
-    Aref = np.zeros_like(A)
+    Aref = np.zeros((m.n_dof, m.n_dof))
     Aref[np.repeat(np.arange(m.n_dof), np.diff(rp)), ci] = v
-    assert np.abs(A - Aref).max() <= 1e-13 * np.abs(Aref).max()
-    # contributions are element-ascending within each nonzero (deterministic order)
-    e_of = (p.csrc & 0x7fffffff) // 55
+    rows = (3 * p.node_gid[:p.n_own, None] + np.arange(3)).ravel()
+    assert np.abs(A - Aref[rows]).max() <= 1e-13 * np.abs(Aref).max()
+    # contributions are in ascending GLOBAL element id within each nonzero (the reference's order)
+    e_of = p.elem_gid[(p.csrc & 0x7fffffff) // 55]
     for k in range(0, p.nnzb, 97):
         seg = e_of[p.cptr[k]:p.cptr[k + 1]]
         assert np.all(np.diff(seg.astype(np.int64)) >= 0)
+
+
+def test_sell_layout_is_a_faithful_copy_of_the_block_csr():
+    m = block_model((4, 5, 3))
+    p = fg.Plan(m.nodes, m.conn)
+    assert p.n_slices == (p.n_own + 31) // 32 and p.slice_ptr[-1] == p.n_slots
+    assert np.all(np.diff(p.slice_ptr) % 32 == 0)
+    live = p.sell_row[p.sell_row >= 0]
+    assert sorted(live) == list(range(p.n_own))                  # every row sits in exactly one lane
+    lens = np.diff(p.browptr)
+    seen = 0
+    for s in range(p.n_slices):
+        width = (p.slice_ptr[s + 1] - p.slice_ptr[s]) // 32
+        rows = p.sell_row[32 * s:32 * s + 32]
+        assert width == max(lens[r] for r in rows if r >= 0)
+        for lane, r in enumerate(rows):
+            slots = p.slice_ptr[s] + 32 * np.arange(width) + lane
+            if r < 0:
+                assert np.all(np.diff(p.scptr[np.r_[slots, slots[-1] + 1]]) >= 0)
+                continue
+            n = lens[r]
+            assert np.array_equal(p.sbcol[slots[:n]], p.bcol[p.browptr[r]:p.browptr[r + 1]])
+            assert np.all(p.sbcol[slots[n:]] == r)               # padding points at the row itself
+            for j in range(n):
+                a, b = p.scptr[slots[j]], p.scptr[slots[j] + 1]
+                q = p.browptr[r] + j
+                assert np.array_equal(p.scsrc[a:b], p.csrc[p.cptr[q]:p.cptr[q + 1]])
+                seen += b - a
+            assert all(p.scptr[t] == p.scptr[t + 1] for t in slots[n:])
+            jd = list(p.bcol[p.browptr[r]:p.browptr[r + 1]]).index(r)
+            assert p.sdiag[r] == 9 * (p.slice_ptr[s] + 32 * jd) + lane
+    assert seen == p.n_contrib
+    assert p.n_slots / p.nnzb < 1.15                             # sigma-sorting keeps padding small
 
 
 def test_kuhn_block_counts_and_geometry():
@@ -88,10 +126,10 @@ def test_partition_halo_lists_are_consistent(nranks):
     assert np.abs(np.bincount(owner, minlength=nranks) - len(m.nodes) / nranks).max() <= 1
     f = lambda gid: 1000.0 + 3.0 * gid                      # noqa: E731  value carried by node gid
     for r, p in enumerate(plans):
-        assert np.all(owner[p.node_gid[:p.n_own]] == r) and np.all(np.diff(p.node_gid[:p.n_own]) > 0)
+        assert np.all(owner[p.node_gid[:p.n_own]] == r) and len(set(p.node_gid[:p.n_own])) == p.n_own
         # every element touching an owned node is local, with all its nodes present
         touch = np.where((owner[m.conn] == r).any(axis=1))[0]
-        assert np.array_equal(touch, p.elem_gid)
+        assert np.array_equal(touch, np.sort(p.elem_gid))
         assert set(np.unique(m.conn[touch])) == set(p.node_gid)
         for i, q in enumerate(p.nbr_rank):
             pq = plans[q]

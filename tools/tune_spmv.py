@@ -11,10 +11,10 @@ g = fg.FeaGpu(mb["nodes"], mb["conn"], 0, 100.0, 100.0, 5, mb["presc_node"], mb[
 cnt = g.counts()
 g.apply_increment(1.0); g.assemble_all(True); g.apply_bc(0.0)
 bytes_ = 76.0 * cnt["nnzb"] + 60.0 * cnt["owned_nodes"]
-for lpr in (4, 8, 16, 32):
-    g.set_param("spmv_lpr", lpr)
+print("sell padding:", cnt["sell_slots"] / cnt["nnzb"])
+for rep in range(3):
     ms = g.bench_spmv(50)
-    print(f"lpr {lpr:2d}: {ms:.4f} ms  {bytes_ / ms / 1e6:.0f} GB/s")
+    print(f"spmv: {ms:.4f} ms  {bytes_ / ms / 1e6:.0f} GB/s (algorithmic BSR bytes)")
 for rep in range(3):
     g.assemble_all(True); g.apply_bc(0.0)
     print({k: round(v, 4) for k, v in g.phase_ms().items() if isinstance(v, float)})
