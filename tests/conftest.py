@@ -59,3 +59,32 @@ def block_model(n, model=1, bc_style=0, dy=0.0, box=(1.0, 1.0, 1.0), y0=0.0):
     mb = fg.mesh_block(nx, ny, nz, box[0], box[1], box[2], y0, bc_style, dy)
     return Model(nodes=mb["nodes"], conn=mb["conn"], presc_node=mb["presc_node"], presc_type=mb["presc_type"],
                  presc_vals=mb["presc_vals"], model=model, lam=100.0, mu=100.0, gauss=5)
+
+
+def write_sexp(path, m, load_increments=2, shuffle_keys=False):
+    """Write an oracle Model as a task file in the reference's .sexp grammar
+    (utilities/exporter.py:442-502 is the reference's writer; ids are 0-based)."""
+    name = "COMPRESSIBLE_NEOHOOKEAN" if m.model == 1 else "A5"
+    solver = {0: "CG", 1: "PCG_ILU", 2: "CHOLESKY"}[m.solver_type]
+    with open(path, "w") as f:
+        f.write(";; -*- Mode: lisp; -*-\n(task\n")
+        f.write(f" (model :name {name}\n        (model-parameters :mu {m.mu:g} :lambda {m.lam:g}))\n")
+        if shuffle_keys:   # key order is free; symbols are case-insensitive; ';' comments
+            f.write(f" (solution :max-newton-count {m.max_newton} :modified-newton {'Yes' if m.modified_newton else 'no'} ; comment\n"
+                    f"   :load-increments-count {load_increments} :task-type cartesian3d :desired-tolerance {float(m.desired_tolerance)!r}\n")
+        else:
+            f.write(f" (solution :desired-tolerance {float(m.desired_tolerance)!r} :task-type CARTESIAN3D "
+                    f":load-increments-count {load_increments} :modified-newton {'yes' if m.modified_newton else 'no'} "
+                    f":max-newton-count {m.max_newton}\n")
+        f.write(f"   (element-type :gauss-nodes-count {m.gauss} :name TETRAHEDRA10 :nodes-count 10)\n")
+        f.write(f"   (slae-solver :type {solver} :tolerance {float(m.solver_tolerance)!r} :max-iterations {m.solver_max_iter})\n")
+        f.write("   (line-search :max 0)\n   (arc-length :max 0))\n (input-data\n  (geometry\n   (nodes\n")
+        for x in m.nodes:
+            f.write(f"    ({float(x[0])!r} {float(x[1])!r} {float(x[2])!r})\n")
+        f.write("   )\n   (elements\n")
+        for c in m.conn:
+            f.write("    (" + " ".join(str(int(v)) for v in c) + ")\n")
+        f.write("   ))\n  (boundary-conditions\n   (prescribed-displacements\n")
+        for n, t, v in zip(m.presc_node, m.presc_type, m.presc_vals):
+            f.write(f"    (presc-node :y {float(v[1])!r} :x {float(v[0])!r} :z {float(v[2])!r} :type {int(t)} :node-id {int(n)})\n")
+        f.write("   ))))\n")

@@ -70,6 +70,11 @@ def main():
             R_bc=R_bc, Kv_bc=Kv_bc, u_first=u,
             newton_tol=tol, newton_u_head=sol[:3], newton_u_sum=sol.sum(axis=0), newton_count=len(sol))
         print(name, "nnz", len(v), "newton solves", len(sol), "final tol", tol[-1])
+        if name == "neohook_brick_analytical":
+            # the reference's own Gmsh export of those two increments (fea_solver.c:1375-1488)
+            import gzip
+            with open("/tmp/fea_ref_out.msh", "rb") as f, gzip.open(os.path.join(OUT, name + "_2steps.msh.gz"), "wb") as g:
+                g.write(f.read())
 
     # fea_model.c on bare deformation gradients (both models)
     Fs = np.eye(3)[None] + 0.2 * rng.standard_normal((16, 3, 3))
