@@ -43,6 +43,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL's version banner, for one) write to stdout; the contract is ONE JSON line
+# there.  Keep the real stdout aside and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -176,7 +187,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world, note=None):
@@ -390,7 +401,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": 1, "kind": kind,
                                 "sample": f"one pass over a Kuhn sub-block of {n_s}^3 cubes ({ne} tets) in the same state, "
                                           f"{sec:.1f} s on one host core (the reference is single-threaded)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

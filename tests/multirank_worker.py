@@ -1,0 +1,83 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_multirank.py or by hand):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multirank_worker.py
+Every rank drives its fea_gpu context through a Newton step (NCCL halo exchange + all-reduced
+dots); rank 0 repeats the computation on a single-rank context and on the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "fea-large_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def main():
+    import torch.distributed as dist
+    import fea_gpu as fg
+    from conftest import block_model
+    from oracle.oracle import PortOracle
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    box = [fg.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+
+    m = block_model((4, 4 * world + 1, 4), model=1, bc_style=1, dy=0.02)
+    rng = np.random.default_rng(3)
+    x0 = m.nodes + 0.004 * rng.standard_normal(m.nodes.shape)
+    g = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals,
+                  rank=rank, nranks=world, nccl_id=box[0], device=local)
+    cnt = g.counts()
+    assert cnt["neighbours"] >= 1 and cnt["halo_recv"] > 0
+    g.set_nodes(x0)
+    g.apply_increment(1.0)
+    g.assemble_all(True)
+    R0 = g.get_forces()                      # collective all-gather
+    g.apply_bc(0.0)
+    it, rr, ok = g.solve(1e-13, 20000)
+    tol = g.dot_R_u()
+    u = g.get_solution()
+    g.update_nodes()                         # x += u, then halo exchange of x
+    g.assemble_all(True)
+    x1 = g.get_nodes()
+    R1 = g.get_forces()
+    F, S = g.get_state()                     # only owned elements are written
+    Ssum = np.zeros_like(S)
+    import torch
+    t = torch.from_numpy(S.copy()); dist.all_reduce(t); Ssum = t.numpy()   # each element owned once
+    status = {"ok": True}
+    if rank == 0:
+        s1 = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals, device=local)
+        s1.set_nodes(x0); s1.apply_increment(1.0); s1.assemble_all(True)
+        e = {"R0": relmax(R0, s1.get_forces())}
+        s1.apply_bc(0.0)
+        it1, rr1, ok1 = s1.solve(1e-13, 20000)
+        e["u"] = relmax(u, s1.get_solution())
+        e["tol"] = abs(tol - s1.dot_R_u()) / abs(tol)
+        s1.update_nodes(); s1.assemble_all(True)
+        e["x1"] = relmax(x1 - m.nodes, s1.get_nodes() - m.nodes)
+        e["R1"] = relmax(R1, s1.get_forces())
+        e["S"] = relmax(Ssum, s1.get_state()[1])
+        o = PortOracle(m)
+        o.set_nodes(x0); o.apply_increment(1.0); o.update_state(); o.assemble_stiffness(); o.assemble_residual()
+        e["R0_oracle"] = relmax(R0, o.get_forces())
+        o.apply_bc(0.0); o.solve_slae()
+        e["u_oracle"] = relmax(u, o.get_solution())
+        print("MULTIRANK", world, "ranks, pcg its", it, it1, "errors", {k: f"{v:.2e}" for k, v in e.items()}, flush=True)
+        good = ok and ok1 and e["R0"] < 1e-12 and e["R1"] < 1e-9 and e["u"] < 1e-9 and e["x1"] < 1e-9 \
+            and e["S"] < 1e-9 and e["R0_oracle"] < 1e-12 and e["u_oracle"] < 1e-9 and e["tol"] < 1e-9
+        status["ok"] = bool(good)
+        print("MULTIRANK_RESULT", "PASS" if good else "FAIL", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if status["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -177,5 +177,8 @@ def test_feasolver_reports_nonconvergence_like_the_reference(host, tmp_path):
     run = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
     assert run.returncode == 0
     assert "Unable to finish load step in 2 Newton iterations,exit" in run.stdout
+    assert "Load increment 1 finished" in run.stdout and "Load increment 2 finished" not in run.stdout
     msh = open(str(tmp_path / "stuck.msh")).read()
-    assert msh.count("$NodeData") == 1            # only the undeformed step 0 is exported
+    # current_load_step is rolled back to -1, so the reference's export loop (load <= step,
+    # :1440) writes the mesh and no data sections at all
+    assert msh.count("$Nodes") == 1 and msh.count("$NodeData") == 0
