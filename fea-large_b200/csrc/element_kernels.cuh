@@ -79,18 +79,29 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   const bool live = e < A.n_elems;
   double *my = sm + (size_t)gp * NFIELD * 32 + lane;  // field f at my[f*32]
 
+  // ------------------------------ phase 0 ------------------------------------
+  // the NG warps of the CTA fetch the 10 nodes of the 32 elements once (coalesced connectivity,
+  // gathered coordinates) into the region the store tiles will use later: [node][x0..2,X0..2][lane]
+  double *coords = sm + (size_t)NG * NFIELD * 32;
+  for (int a = gp; a < 10; a += NG) {
+    const int node = live ? A.conn_soa[(size_t)a * A.ne_pad + e] : 0;
+    const double *xk = A.x + 3 * (size_t)node, *Xk = A.X0 + 3 * (size_t)node;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      coords[((a * 6 + d) * 32) + lane] = xk[d];
+      coords[((a * 6 + 3 + d) * 32) + lane] = Xk[d];
+    }
+  }
+  __syncthreads();
+
   // ------------------------------ phase A ------------------------------------
   {
-    int node[10];
-#pragma unroll
-    for (int a = 0; a < 10; ++a) node[a] = live ? A.conn_soa[(size_t)a * A.ne_pad + e] : 0;
-
     // J[i][j] = sum_k dN_k/dxi_i * x_k,j      (fea_solver.c:690-696)
     double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-      const double *xk = A.x + 3 * (size_t)node[k];
-      const double x0 = xk[0], x1 = xk[1], x2 = xk[2];
+      const double x0 = coords[(k * 6 + 0) * 32 + lane], x1 = coords[(k * 6 + 1) * 32 + lane],
+                   x2 = coords[(k * 6 + 2) * 32 + lane];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const double d = c_tab.dN[gp][i][k];
@@ -117,8 +128,8 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     double Fi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-      const double *Xk = A.X0 + 3 * (size_t)node[k];
-      const double X0 = Xk[0], X1 = Xk[1], X2 = Xk[2];
+      const double X0 = coords[(k * 6 + 3) * 32 + lane], X1 = coords[(k * 6 + 4) * 32 + lane],
+                   X2 = coords[(k * 6 + 5) * 32 + lane];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         Fi[0][j] = fma(g[j][k], X0, Fi[0][j]);

@@ -77,6 +77,7 @@ struct fea_gpu_ctx {
   int64_t n_slots = 0;
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
+  int gather_threads = 256;
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;
@@ -577,8 +578,8 @@ static fea::SellMat sell_mat(fea_gpu_ctx *c) {
 
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
-  const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), 148 * 32);
-  fea::gather_blocks_kernel<<<grid, 256, 0, c->stream>>>(sell_mat(c), c->cptr, c->csrc, c->Ke,
+  const int grid = c->plan.n_slices;   // one CTA per slice, dispatched in slice order (L2 locality)
+  fea::gather_blocks_kernel<<<grid, c->gather_threads, 0, c->stream>>>(sell_mat(c), c->cptr, c->csrc, c->Ke,
                                                          with_bc ? c->pflag : nullptr);
   LAUNCHED();
   phase_end(c, PH_GATHER_K);
@@ -966,7 +967,8 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   if (!c || !name) return FEA_GPU_ERR_ARG;
   const std::string k(name);
   const int v = (int)value;
-  if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
+  if (k == "gather_threads" && (v == 64 || v == 128 || v == 256)) c->gather_threads = v;
+  else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else {
     g_err = "unknown parameter or value out of range: " + k;

@@ -18,3 +18,8 @@ for rep in range(3):
 for rep in range(3):
     g.assemble_all(True); g.apply_bc(0.0)
     print({k: round(v, 4) for k, v in g.phase_ms().items() if isinstance(v, float)})
+for gt in (64, 128, 256):
+    g.set_param("gather_threads", gt)
+    for rep in range(2):
+        g.assemble_all(True)
+    print("gather_threads", gt, {k: round(v, 4) for k, v in g.phase_ms().items() if k in ("element", "gather_k")})
