@@ -39,6 +39,20 @@ def load_golden(name):
     return m, z
 
 
+def load_brick_fine():
+    """The reference's unstructured 22 934-tet model with the BC ids fixed (see make_golden.py)."""
+    from oracle.oracle import Model
+    z = np.load(os.path.join(GOLDEN, "brick_fine.npz"))
+    m = Model(nodes=np.ascontiguousarray(z["nodes_nano"] / 1e9), conn=np.ascontiguousarray(z["conn"]),
+              presc_node=np.ascontiguousarray(z["presc_node"]), presc_type=np.ascontiguousarray(z["presc_type"]),
+              presc_vals=np.ascontiguousarray(z["presc_vals"]), model=int(z["model"]), lam=float(z["lam"]),
+              mu=float(z["mu"]), gauss=int(z["gauss"]), load_increments=1, desired_tolerance=1e-6,
+              modified_newton=True, max_newton=1, solver_type=0)
+    x = m.nodes.copy()
+    x[:, 1] = 1.0 + (x[:, 1] - 1.0) * 1.01          # the 1 % stretched state the golden was taken on
+    return m, z, x
+
+
 @pytest.fixture(params=BRICKS)
 def brick(request):
     m, z = load_golden(request.param)

@@ -73,8 +73,9 @@ def main():
         if name == "neohook_brick_analytical":
             # the reference's own Gmsh export of those two increments (fea_solver.c:1375-1488)
             import gzip
-            with open("/tmp/fea_ref_out.msh", "rb") as f, gzip.open(os.path.join(OUT, name + "_2steps.msh.gz"), "wb") as g:
-                g.write(f.read())
+            with open("/tmp/fea_ref_out.msh", "rb") as f, open(os.path.join(OUT, name + "_2steps.msh.gz"), "wb") as raw:
+                with gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as g:   # mtime=0: reproducible bytes
+                    g.write(f.read())
 
     # fea_model.c on bare deformation gradients (both models)
     Fs = np.eye(3)[None] + 0.2 * rng.standard_normal((16, 3, 3))
@@ -90,5 +91,40 @@ def main():
     print("model_tables:", len(Fs), "deformation gradients")
 
 
+
+
+def brick_fine_fixture():
+    """solver-large/data/brick_fine.sexp as arrays (34 070 nodes, 22 934 tets, unstructured), with
+    the BC node ids shifted by -1: as shipped they are 1-based while the loader reads them 0-based
+    (SURVEY 8c "fixture defect").  Reference-compiled probes pin K and R on the 1 % stretched state."""
+    m = load_sexp(os.path.join(DATA, "brick_fine.sexp"))
+    m.presc_node = (m.presc_node - 1).astype(np.int32)
+    x = m.nodes.copy()
+    x[:, 1] = 1.0 + (x[:, 1] - 1.0) * 1.01
+    r = RefOracle(m)
+    r.set_nodes(x)
+    r.update_state()
+    r.assemble_stiffness()
+    r.assemble_residual()
+    rp, ci, v = r.get_csr()
+    rng = np.random.default_rng(77)
+    probes = rng.standard_normal((2, m.n_dof))
+    Kv = np.stack([csr_mv(rp, ci, v, p) for p in probes])
+    F, S = r.get_state()
+    # kept small: coordinates are 9-decimal in the file -> exact as integer nano-units; K and R are
+    # pinned through every 40th entry of K.v / R plus their norms (the probe is regenerated from
+    # its seed); the entry-wise check is done live against oracle/oracle_fea.c
+    micro = np.rint(m.nodes * 1e9).astype(np.int64)       # the file carries 9 decimals
+    assert np.array_equal(micro / 1e9, m.nodes)
+    np.savez_compressed(os.path.join(OUT, "brick_fine.npz"), nodes_nano=micro,
+                        conn=m.conn, presc_node=m.presc_node, presc_type=m.presc_type, presc_vals=m.presc_vals,
+                        model=m.model, lam=m.lam, mu=m.mu, gauss=m.gauss, nnz=len(v), max_row=int(np.diff(rp).max()),
+                        probe_seed=77, Kv_sample=Kv[:, ::40], Kv_norm=np.linalg.norm(Kv, axis=1),
+                        R_sample=r.get_forces()[::40], R_norm=np.linalg.norm(r.get_forces()),
+                        S_mean=S.mean(axis=(0, 1)), S_sample=S[::997])
+    print("brick_fine nnz", len(v), "max row", np.diff(rp).max())
+
+
 if __name__ == "__main__":
     main()
+    brick_fine_fixture()

@@ -261,3 +261,48 @@ def test_large_block_properties():
     u, Rb = g.get_solution(), g.get_forces()
     assert ok and np.linalg.norm(g.spmv(u) - Rb) <= 2e-10 * np.linalg.norm(Rb)
     assert g.counts()["nnzb"] * 9 / m.n_dof > 80                      # ~81-86 nnz/row
+
+
+def test_brick_fine_unstructured_vs_oracle():
+    """The reference's largest shipped model (unstructured, rows up to 330 nonzeros): pattern and
+    every value of K, R and sigma against the oracle; PCG residual checked with the device SpMV."""
+    from conftest import load_brick_fine
+    m, z, x = load_brick_fine()
+    g, o = make_gpu(m), PortOracle(m)
+    for s_ in (g, o):
+        s_.set_nodes(x); s_.update_state(); s_.assemble_stiffness(); s_.assemble_residual()
+    rows, rp, ci, v = g.get_csr()
+    rpo, cio, vo = o.get_csr()
+    assert len(v) == 8300196 and np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+    assert relmax(v, vo) < RTOL_ELEM
+    assert relmax(g.get_forces(), o.get_forces()) < RTOL_ELEM
+    assert relmax(g.get_state()[1], o.get_state()[1]) < RTOL_ELEM
+    assert relmax(g.get_forces()[::40], z["R_sample"]) < RTOL_ELEM          # reference-compiled pin
+    cnt = g.counts()
+    assert cnt["sell_slots"] / cnt["nnzb"] < 1.2                            # padding on an irregular mesh
+    g.apply_increment(1.0); g.assemble_all(True); g.apply_bc(0.0)
+    it, rr, ok = g.solve(1e-12, 20000)
+    u, Rb = g.get_solution(), g.get_forces()
+    assert ok and np.linalg.norm(g.spmv(u) - Rb) <= 5e-12 * np.linalg.norm(Rb)
+
+
+@pytest.mark.parametrize("model,closed", [(1, uniaxial_neohookean), (0, uniaxial_a5)])
+def test_large_strain_uniaxial_sweep_to_stretch_2(model, closed):
+    """BASELINE configs[4] in small: 120 load increments of L/120 (as the shipped files: 0.05 on a
+    length of 6) up to stretch 2.0, full Newton each increment; the homogeneous state must follow
+    the closed forms of exact-solutions/uniaxial all the way."""
+    m = block_model((3, 3, 3), model=model, bc_style=0, dy=1.0 / 120)
+    g = make_gpu(m)
+    checks = {1, 30, 60, 90, 120}
+    for step in range(1, 121):
+        us, tols = newton_gpu(g, 1, 1e-16, False, 40 if model == 1 else 80)
+        assert abs(tols[-1]) <= 1e-16, (step, tols[-1])
+        if step in checks:
+            k1 = 1.0 + step / 120.0
+            k2, sig = closed(k1)
+            F, S = g.get_state()
+            assert np.allclose(S[:, :, 1, 1], sig, rtol=1e-8), step
+            assert np.allclose(F[:, :, 1, 1], k1, rtol=1e-10) and np.allclose(F[:, :, 0, 0], k2, rtol=1e-8), step
+            assert g.bad_points() == 0
+    x = g.get_nodes()
+    assert np.isclose(x[:, 1].max(), 2.0, rtol=1e-12)

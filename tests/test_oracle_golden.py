@@ -112,3 +112,20 @@ def test_closed_form_table_values():
     for s, k2e, se in [(1, 0.997905793, 2.118310408), (2, 0.995789748, 4.307607909), (3, 0.993651725, 6.569473018)]:
         k2, sig = uniaxial_a5(1 + s * 0.05 / 6)
         assert abs(k2 - k2e) < 1e-9 and abs(sig - se) < 1e-8
+
+
+def test_brick_fine_unstructured_mesh_matches_reference_compiled():
+    """C1f: 102 210 DOF, 8 300 196 nonzeros (81.2 per row, max 330) -- SURVEY section 8."""
+    from conftest import load_brick_fine
+    m, z, x = load_brick_fine()
+    o = PortOracle(m)
+    o.set_nodes(x); o.update_state(); o.assemble_stiffness(); o.assemble_residual()
+    rp, ci, v = o.get_csr()
+    assert len(v) == int(z["nnz"]) == 8300196 and int(np.diff(rp).max()) == int(z["max_row"]) == 330
+    probes = np.random.default_rng(int(z["probe_seed"])).standard_normal((2, m.n_dof))
+    for p, ks, kn in zip(probes, z["Kv_sample"], z["Kv_norm"]):
+        kv = csr_mv(rp, ci, v, p)
+        assert np.allclose(kv[::40], ks, rtol=0, atol=1e-12 * np.abs(ks).max()) and abs(np.linalg.norm(kv) - kn) <= 1e-12 * kn
+    R = o.get_forces()
+    assert np.array_equal(R[::40], z["R_sample"]) and abs(np.linalg.norm(R) - float(z["R_norm"])) <= 1e-13 * float(z["R_norm"])
+    assert np.array_equal(o.get_state()[1][::997], z["S_sample"])
