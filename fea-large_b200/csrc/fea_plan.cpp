@@ -561,3 +561,101 @@ extern "C" int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, dou
   }
   return FEA_GPU_OK;
 }
+
+// Hollow cylinder: the Kuhn split of fea_mesh_block applied in (r, theta, z) index space, periodic
+// in theta.  Every Kuhn edge joins vertex v and v + m with m a 0/1 vector, so a half-grid node with
+// odd-coordinate mask m is the midpoint of the straight edge between (node - m) and (node + m).
+extern "C" int fea_mesh_cylinder(int32_t nr, int32_t nt, int32_t nz, double r_in, double r_out, double length,
+                                 double delta, int64_t *n_nodes, int64_t *n_elems, int64_t *n_presc,
+                                 double *nodes, int32_t *conn, int32_t *presc_node, int32_t *presc_type,
+                                 double *presc_vals) {
+  if (nr < 1 || nt < 3 || nz < 1 || !(r_in > 0.0) || !(r_out > r_in) || !(length > 0.0)) return FEA_GPU_ERR_ARG;
+  const int64_t pr = 2 * (int64_t)nr + 1, pt = 2 * (int64_t)nt, pz = 2 * (int64_t)nz + 1;
+  const int64_t nn = pr * pt * pz, ne = 6 * (int64_t)nr * nt * nz;
+  if (nn >= 0x7fffffff || ne >= 0x7fffffff) return FEA_GPU_ERR_ARG;
+  auto nid = [&](int64_t ir, int64_t jt, int64_t kz) {
+    return (int32_t)((kz * pt + ((jt % pt + pt) % pt)) * pr + ir);
+  };
+  const double two_pi = 6.283185307179586476925286766559;
+  auto vertex = [&](int64_t ir, int64_t jt, int64_t kz, double *x) {   // all indices even
+    const double r = r_in + (r_out - r_in) * (double)(ir / 2) / (double)nr;
+    const double th = two_pi * (double)(((jt % pt + pt) % pt) / 2) / (double)nt;
+    x[0] = r * std::cos(th);
+    x[1] = r * std::sin(th);
+    x[2] = length * (double)(kz / 2) / (double)nz;
+  };
+  // prescribed nodes: inner + outer wall (all theta, z), plus the interior of the two end faces
+  int64_t np = 0;
+  for (int64_t kz = 0; kz < pz; ++kz)
+    for (int64_t jt = 0; jt < pt; ++jt)
+      for (int64_t ir = 0; ir < pr; ++ir)
+        if (ir == 0 || ir == pr - 1 || kz == 0 || kz == pz - 1) ++np;
+  if (n_nodes) *n_nodes = nn;
+  if (n_elems) *n_elems = ne;
+  if (n_presc) *n_presc = np;
+  if (nodes) {
+#pragma omp parallel for schedule(static)
+    for (int64_t kz = 0; kz < pz; ++kz)
+      for (int64_t jt = 0; jt < pt; ++jt)
+        for (int64_t ir = 0; ir < pr; ++ir) {
+          const int64_t mr = ir & 1, mt = jt & 1, mz = kz & 1;
+          double a[3], b[3];
+          vertex(ir - mr, jt - mt, kz - mz, a);
+          vertex(ir + mr, jt + mt, kz + mz, b);
+          double *x = nodes + 3 * (size_t)nid(ir, jt, kz);
+          for (int d = 0; d < 3; ++d) x[d] = 0.5 * (a[d] + b[d]);
+        }
+  }
+  if (conn) {
+    static const int perm[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    static const int edge[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+#pragma omp parallel for schedule(static)
+    for (int64_t cz = 0; cz < nz; ++cz)
+      for (int64_t ct = 0; ct < nt; ++ct)
+        for (int64_t cr = 0; cr < nr; ++cr) {
+          const int64_t cell = (cz * nt + ct) * nr + cr;
+          for (int t = 0; t < 6; ++t) {
+            int64_t v[4][3];   // (ir, jt, kz) in doubled indices
+            v[0][0] = 2 * cr; v[0][1] = 2 * ct; v[0][2] = 2 * cz;
+            for (int s = 0; s < 3; ++s) {
+              for (int d = 0; d < 3; ++d) v[s + 1][d] = v[s][d];
+              v[s + 1][perm[t][s]] += 2;
+            }
+            // (r, theta, z) -> (x, y, z) preserves orientation, so the sign test works in index space
+            int64_t a[3][3];
+            for (int r = 0; r < 3; ++r)
+              for (int d = 0; d < 3; ++d) a[r][d] = v[r + 1][d] - v[0][d];
+            const int64_t det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
+                                a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                                a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+            if (det < 0)
+              for (int d = 0; d < 3; ++d) std::swap(v[1][d], v[2][d]);
+            int32_t *c = conn + (size_t)(cell * 6 + t) * 10;
+            for (int k = 0; k < 4; ++k) c[k] = nid(v[k][0], v[k][1], v[k][2]);
+            for (int k = 0; k < 6; ++k) {
+              const int64_t *p0 = v[edge[k][0]], *p1 = v[edge[k][1]];
+              c[4 + k] = nid((p0[0] + p1[0]) / 2, (p0[1] + p1[1]) / 2, (p0[2] + p1[2]) / 2);
+            }
+          }
+        }
+  }
+  if (nodes && presc_node && presc_type && presc_vals) {
+    int64_t k = 0;
+    for (int64_t kz = 0; kz < pz; ++kz)
+      for (int64_t jt = 0; jt < pt; ++jt)
+        for (int64_t ir = 0; ir < pr; ++ir) {
+          const bool wall_in = ir == 0, wall_out = ir == pr - 1, face = kz == 0 || kz == pz - 1;
+          if (!(wall_in || wall_out || face)) continue;
+          const int32_t id = nid(ir, jt, kz);
+          const double *x = nodes + 3 * (size_t)id;
+          const double r = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+          presc_node[k] = id;
+          presc_type[k] = ((wall_in || wall_out) ? 3 : 0) | (face ? 4 : 0);
+          presc_vals[3 * k + 0] = wall_in ? delta * x[0] / r : 0.0;
+          presc_vals[3 * k + 1] = wall_in ? delta * x[1] / r : 0.0;
+          presc_vals[3 * k + 2] = 0.0;
+          ++k;
+        }
+  }
+  return FEA_GPU_OK;
+}

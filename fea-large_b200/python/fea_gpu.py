@@ -34,7 +34,7 @@ SYMBOLS = [
     "fea_gpu_counts", "fea_gpu_launch_count", "fea_gpu_timer_start", "fea_gpu_timer_stop",
     "fea_gpu_sync", "fea_gpu_phase_ms", "fea_gpu_bench_spmv", "fea_gpu_measure_peaks",
     "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
-    "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_mesh_block",
+    "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_mesh_block", "fea_mesh_cylinder",
 ]
 
 _lib = None
@@ -92,6 +92,23 @@ def mesh_block(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, y0=0.0, bc_style=0, dy=0.0):
     pt = np.empty(npz.value, np.int32)
     pv = np.empty((npz.value, 3))
     _check(f(nx, ny, nz, lx, ly, lz, y0, bc_style, dy, None, None, None, nodes.ctypes.data, conn.ctypes.data,
+             pn.ctypes.data, pt.ctypes.data, pv.ctypes.data))
+    return dict(nodes=nodes, conn=conn, presc_node=pn, presc_type=pt, presc_vals=pv)
+
+
+def mesh_cylinder(nr, nt, nz, r_in=1.0, r_out=2.0, length=1.0, delta=0.0):
+    """Hollow cylinder about z with prescribed radial wall displacement (see fea_mesh_cylinder)."""
+    f = lib().fea_mesh_cylinder
+    f.argtypes = [C.c_int32] * 3 + [C.c_double] * 4 + [C.c_void_p] * 8
+    nn, ne, npz = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    _check(f(nr, nt, nz, r_in, r_out, length, delta, C.addressof(nn), C.addressof(ne), C.addressof(npz),
+             None, None, None, None, None))
+    nodes = np.empty((nn.value, 3))
+    conn = np.empty((ne.value, 10), np.int32)
+    pn = np.empty(npz.value, np.int32)
+    pt = np.empty(npz.value, np.int32)
+    pv = np.empty((npz.value, 3))
+    _check(f(nr, nt, nz, r_in, r_out, length, delta, None, None, None, nodes.ctypes.data, conn.ctypes.data,
              pn.ctypes.data, pt.ctypes.data, pv.ctypes.data))
     return dict(nodes=nodes, conn=conn, presc_node=pn, presc_type=pt, presc_vals=pv)
 

@@ -215,6 +215,17 @@ int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, dou
                    int64_t *n_elems, int64_t *n_presc, double *nodes, int32_t *conn,
                    int32_t *presc_node, int32_t *presc_type, double *presc_vals);
 
+/* Thick-walled hollow cylinder about the z axis (BASELINE configs[1], the Lame problem of
+ * exact-solutions/lame): nr x nt x nz cells in (r, theta, z), each cut into 6 Kuhn tets with
+ * straight edges (mid-side nodes at edge midpoints, as every shipped mesh).  Nodes
+ * (2nr+1)(2nt)(2nz+1), tets 6 nr nt nz.  Boundary conditions, per load increment: inner wall
+ * r = r_in moves radially by `delta` (x and y prescribed), outer wall r = r_out is held in x and
+ * y, both end faces are held in z (plane strain).  Call with NULL arrays for sizes. */
+int fea_mesh_cylinder(int32_t nr, int32_t nt, int32_t nz, double r_in, double r_out, double length,
+                      double delta, int64_t *n_nodes, int64_t *n_elems, int64_t *n_presc,
+                      double *nodes, int32_t *conn, int32_t *presc_node, int32_t *presc_type,
+                      double *presc_vals);
+
 #ifdef __cplusplus
 }
 #endif

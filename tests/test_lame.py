@@ -1,0 +1,89 @@
+"""BASELINE configs[1]: Lame thick cylinder with prescribed radial displacement.
+
+The reference's exact-solutions/lame holds no compressible, displacement-driven finite-strain
+solution; what it does give is the classical small-strain field u(r) = A r + B / r
+(the form behind lame_small.m:43).  For pure displacement data that field does not depend on the
+material constants, so it pins the small-strain limit of both models; at finite wall displacement
+the CUDA path is pinned against the CPU oracle on the same mesh."""
+import numpy as np
+import pytest
+
+import fea_gpu as fg
+from oracle.oracle import Model, PortOracle
+
+A_IN, B_OUT, LEN = 1.0, 2.0, 1.0
+
+
+def cylinder(nr, nt, nz, delta, model):
+    mb = fg.mesh_cylinder(nr, nt, nz, A_IN, B_OUT, LEN, delta)
+    return Model(nodes=mb["nodes"], conn=mb["conn"], presc_node=mb["presc_node"], presc_type=mb["presc_type"],
+                 presc_vals=mb["presc_vals"], model=model, lam=100.0, mu=100.0, gauss=5)
+
+
+def lame_small_strain(r, delta):
+    A = delta * A_IN / (A_IN ** 2 - B_OUT ** 2)      # u(a) = delta, u(b) = 0
+    return A * r - A * B_OUT ** 2 / r
+
+
+def radial(m, x):
+    u = x - m.nodes
+    r = np.hypot(m.nodes[:, 0], m.nodes[:, 1])
+    ur = (u[:, 0] * m.nodes[:, 0] + u[:, 1] * m.nodes[:, 1]) / r
+    ut = (-u[:, 0] * m.nodes[:, 1] + u[:, 1] * m.nodes[:, 0]) / r
+    return r, ur, ut, u[:, 2]
+
+
+def test_cylinder_mesh_is_well_formed():
+    m = cylinder(3, 24, 2, 1e-3, 1)
+    assert m.nodes.shape == (7 * 48 * 5, 3) and m.conn.shape == (6 * 3 * 24 * 2, 10)
+    assert len(np.unique(m.conn)) == len(m.nodes)
+    X = m.nodes[m.conn]
+    for k, (a, b) in enumerate([(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]):
+        assert np.abs(X[:, 4 + k] - (X[:, a] + X[:, b]) / 2).max() < 1e-15       # straight-sided tet10
+    o = PortOracle(m); o.update_state()
+    g, detJ = o.get_gradients()
+    vol = (detJ * PortOracle.tables(5)[0][:, 0]).sum()
+    assert detJ.min() > 0 and abs(vol / (np.pi * (B_OUT ** 2 - A_IN ** 2) * LEN) - 1) < 0.015   # inscribed polygon
+    r = np.hypot(m.nodes[:, 0], m.nodes[:, 1])
+    wall = m.presc_node[(m.presc_type & 3) == 3]
+    assert set(np.round(r[wall], 2)) <= {0.99, 1.0, 1.98, 1.99, 2.0}
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_oracle_small_strain_limit_is_classical_lame(model):
+    delta = 1e-5
+    m = cylinder(6, 48, 2, delta, model)
+    o = PortOracle(m)
+    o.newton_solve(1, 1e-22, False, 15)
+    r, ur, ut, uz = radial(m, o.get_nodes())
+    assert np.abs(ur - lame_small_strain(r, delta)).max() < 5e-3 * delta     # chord error of a 48-gon
+    assert np.abs(ut).max() < 2e-3 * delta and np.abs(uz).max() < 1e-3 * delta
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", [0, 1])
+def test_gpu_lame_cylinder_vs_oracle_and_small_strain(model):
+    from test_gpu_parity import RTOL_ELEM, RTOL_SOLVE, make_gpu, newton_gpu, relmax
+    # small wall displacement: classical Lame
+    delta = 1e-5
+    m = cylinder(6, 48, 2, delta, model)
+    g = make_gpu(m)
+    newton_gpu(g, 1, 1e-22, False, 15)
+    r, ur, ut, uz = radial(m, g.get_nodes())
+    assert np.abs(ur - lame_small_strain(r, delta)).max() < 5e-3 * delta
+    # finite wall displacement (10 % of the inner radius over two increments): CUDA path vs oracle
+    m = cylinder(4, 32, 2, 0.05, model)
+    g, o = make_gpu(m), PortOracle(m)
+    for s in (g, o):
+        s.apply_increment(1.0); s.update_state(); s.assemble_stiffness(); s.assemble_residual()
+    assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+    assert relmax(g.get_forces(), o.get_forces()) < RTOL_ELEM
+    g.set_nodes(m.nodes); o.set_nodes(m.nodes)
+    newton_gpu(g, 2, 1e-14, False, 40 if model == 1 else 80)
+    o.newton_solve(2, 1e-14, False, 40 if model == 1 else 80)
+    assert relmax(g.get_nodes() - m.nodes, o.get_nodes() - m.nodes) < RTOL_SOLVE
+    assert relmax(g.get_state()[1], o.get_state()[1]) < 1e-8
+    r, ur, ut, uz = radial(m, g.get_nodes())
+    inner = np.isclose(r, A_IN, atol=2e-2)
+    assert np.allclose(ur[inner & (np.abs(ut) < 1)], 0.10, atol=2e-3) and np.abs(uz).max() < 1e-9
+    assert g.bad_points() == 0
