@@ -86,7 +86,7 @@ struct fea_gpu_ctx {
           *rsrc = nullptr, *sdiag = nullptr;
   uint32_t *csrc = nullptr;
   double *vals = nullptr, *vals_saved = nullptr;
-  double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr;
+  double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr, *u_saved = nullptr;
   uint8_t *pflag = nullptr;
   double *pval = nullptr;
   int32_t *inc_dof = nullptr;
@@ -327,6 +327,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_alloc(&c->q, n3));
   TRY(dev_alloc(&c->r, n3));
   TRY(dev_alloc(&c->dinv, n3));
+  TRY(dev_alloc(&c->u_saved, n3));
   TRY(dev_alloc(&c->partials, 3 * (size_t)MAX_PARTIALS));
   TRY(dev_alloc(&c->counters, 8));
   TRY(dev_alloc(&c->ctl, 1));
@@ -406,7 +407,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (c->has_comm) ncclCommDestroy(c->comm);
   void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->slice_ptr, c->sell_row, c->bcol,
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
-                  c->p, c->q, c->r, c->dinv, c->pflag, c->pval, c->inc_dof, c->inc_val,
+                  c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
                   c->flush, c->export_buf};
   for (void *p : ptrs)
@@ -717,6 +718,8 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
     LAUNCHED();
   }
 
+  // the starting iterate is the first checkpoint
+  CU(cudaMemcpyAsync(c->u_saved, c->u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
   int launched = 0;
   bool done = false;
   while (!done) {
@@ -736,7 +739,7 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
         fea::pcg_control_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
         LAUNCHED();
       }
-      fea::pcg_direction_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, c->r, c->dinv, c->p, c->ctl);
+      fea::pcg_direction_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, c->r, c->dinv, c->p, c->u, c->u_saved, c->ctl);
       LAUNCHED();
     }
     launched += batch;
@@ -744,16 +747,17 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
     CU(cudaStreamSynchronize(c->stream));
     done = c->ctl_host->done || launched >= max_iter;
   }
+  double rr_final = c->ctl_host->rr;
+  if (c->ctl_host->done == 2) {   // stalled or diverged: the checkpoint is the answer (see pcg_step_control)
+    CU(cudaMemcpyAsync(c->u, c->u_saved, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    rr_final = c->ctl_host->rr_saved;
+  }
   phase_end(c, PH_PCG);
   c->last_iters = c->ctl_host->iters;
   if (iters) *iters = c->ctl_host->iters;
-  if (relres) *relres = c->ctl_host->bb > 0.0 ? std::sqrt(c->ctl_host->rr / c->ctl_host->bb) : 0.0;
+  if (relres) *relres = c->ctl_host->bb > 0.0 ? std::sqrt(rr_final / c->ctl_host->bb) : 0.0;
   if (!c->ctl_host->done) {
     g_err = "PCG reached max_iter";
-    return FEA_GPU_ERR_NOT_CONVERGED;
-  }
-  if (!(c->ctl_host->rr == c->ctl_host->rr)) {
-    g_err = "PCG produced NaN";
     return FEA_GPU_ERR_NOT_CONVERGED;
   }
   return FEA_GPU_OK;

@@ -231,7 +231,9 @@ struct PcgCtl {
   double thresh;    // stop when rr <= thresh
   double beta;
   double best_rr;   // smallest r.r seen so far (stagnation guard)
-  int done;         // 1 = tolerance met, 2 = stalled at the rounding floor
+  double rr_saved;  // r.r of the checkpointed iterate (u_saved)
+  int save;         // this iteration's direction kernel must checkpoint u
+  int done;         // 1 = tolerance met, 2 = stalled or diverged: the checkpoint is the answer
   int iters;
   int stall;        // iterations since best_rr last improved
   int stall_limit;
@@ -308,6 +310,8 @@ pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ 
     ctl->beta = 0.0;
     ctl->stall = 0;
     ctl->best_rr = s[2];
+    ctl->rr_saved = s[2];
+    ctl->save = 0;
     if (finalize) {
       ctl->thresh = abs_tol ? tol * tol : tol * tol * s[1];
       ctl->done = (s[1] == 0.0 || s[2] <= ctl->thresh) ? 1 : 0;
@@ -319,21 +323,41 @@ pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ 
 __global__ void pcg_init_finalize_kernel(PcgCtl *ctl, double tol, int abs_tol) {
   ctl->rz_old = ctl->rz_new;
   ctl->best_rr = ctl->rr;
+  ctl->rr_saved = ctl->rr;
+  ctl->save = 0;
   ctl->thresh = abs_tol ? tol * tol : tol * tol * ctl->bb;
   ctl->done = (ctl->bb == 0.0 || ctl->rr <= ctl->thresh) ? 1 : 0;
 }
 
+// Scalar bookkeeping of one CG iteration (one thread).  Besides the recurrences it guards the
+// solve against the two ways CG fails on the reference's "analytical" models, whose K is singular
+// (free rotation about y) so that a right-hand side at rounding level is inconsistent: ||r|| then
+// bottoms out and the iterate is slowly polluted along the null space, finally blowing up.
+//  - every time r.r has halved since the last checkpoint the direction kernel copies u aside
+//    (at most ~100 cheap copies per solve);
+//  - r.r not improving for stall_limit iterations, or exceeding 1e8 x its best, ends the solve
+//    with done = 2 and the host hands back the checkpoint, a clean near-minimum-residual iterate.
 __device__ __forceinline__ void pcg_step_control(PcgCtl *ctl) {
   ctl->beta = ctl->rz_new / ctl->rz_old;
   ctl->rz_old = ctl->rz_new;
   ctl->iters += 1;
-  if (ctl->rr <= ctl->thresh || !(ctl->rr == ctl->rr)) ctl->done = 1;
-  // the residual norm has not improved for stall_limit iterations: r is at the rounding
-  // floor of this system (typical for the last Newton iterations, where b itself is tiny)
+  ctl->save = 0;
+  if (ctl->rr <= ctl->thresh) {
+    ctl->done = 1;
+    return;
+  }
+  if (!(ctl->rr == ctl->rr) || ctl->rr > 1e8 * ctl->best_rr) {   // NaN or diverging
+    ctl->done = 2;
+    return;
+  }
+  if (ctl->rr < 0.5 * ctl->rr_saved) {
+    ctl->rr_saved = ctl->rr;
+    ctl->save = 1;
+  }
   if (ctl->rr < 0.999 * ctl->best_rr) {
     ctl->best_rr = ctl->rr;
     ctl->stall = 0;
-  } else if (++ctl->stall >= ctl->stall_limit && !ctl->done) {
+  } else if (++ctl->stall >= ctl->stall_limit) {
     ctl->done = 2;
   }
 }
@@ -366,14 +390,18 @@ __global__ void pcg_control_kernel(PcgCtl *ctl) {
   if (!ctl->done) pcg_step_control(ctl);
 }
 
-// p = dinv r + beta p
+// p = dinv r + beta p; when the control block asks for it, checkpoint u
 __global__ void __launch_bounds__(256)
 pcg_direction_kernel(int n, const double *__restrict__ r, const double *__restrict__ dinv,
-                     double *__restrict__ p, const PcgCtl *ctl) {
+                     double *__restrict__ p, const double *__restrict__ u, double *__restrict__ u_saved,
+                     const PcgCtl *ctl) {
   if (ctl->done) return;
   const double beta = ctl->beta;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+  const bool save = ctl->save != 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     p[t] = fma(beta, p[t], dinv[t] * r[t]);
+    if (save) u_saved[t] = u[t];
+  }
 }
 
 // out = a . b (fixed order)

@@ -109,8 +109,10 @@ int fea_gpu_restore_stiffness(fea_gpu_handle h);
 /* ---- linear solve and Newton bookkeeping ------------------------------- */
 
 /* solver_solve_slae (:300-321): Jacobi-preconditioned CG on K u = R.
- * Stops when ||r|| <= tol ||b|| (or tol, FEA_SOLVE_ABS_TOL), or when ||r|| has not
- * improved for 200 iterations (rounding floor; still FEA_GPU_OK, relres tells).
+ * Stops when ||r|| <= tol ||b|| (or tol, FEA_SOLVE_ABS_TOL).  If ||r|| stops improving
+ * (rounding floor) or diverges -- K of the reference's "analytical" models is singular, so a
+ * noise-level right-hand side is inconsistent -- the solve ends with the checkpointed
+ * near-minimum-residual iterate; that is still FEA_GPU_OK and `relres` tells what was reached.
  * iters/relres may be NULL.  Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter. */
 int fea_gpu_solve(fea_gpu_handle h, double tol, int32_t max_iter, int32_t flags,
                   int32_t *iters, double *relres);

@@ -85,5 +85,6 @@ def test_gpu_lame_cylinder_vs_oracle_and_small_strain(model):
     assert relmax(g.get_state()[1], o.get_state()[1]) < 1e-8
     r, ur, ut, uz = radial(m, g.get_nodes())
     inner = np.isclose(r, A_IN, atol=2e-2)
-    assert np.allclose(ur[inner & (np.abs(ut) < 1)], 0.10, atol=2e-3) and np.abs(uz).max() < 1e-9
+    # interior nodes are free in z; the Kuhn diagonals break mirror symmetry, so u_z is small, not zero
+    assert np.allclose(ur[inner], 0.10, atol=2e-3) and np.abs(uz).max() < 1e-3 * 0.10
     assert g.bad_points() == 0
