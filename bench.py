@@ -353,7 +353,7 @@ def main():
         newton = {"newton_iters_per_sec": len(nt_ms) / (sum(nt_ms) * 1e-3), "ms_per_newton_iter": float(np.mean(nt_ms)),
                   "pcg_iters_per_newton_iter": float(np.mean(its)), "pcg_relres": float(max(relres)),
                   "pcg_tol": args.lin_tol, "pcg_iters_per_sec": float(sum(its) / (sum(nt_ms) * 1e-3)),
-                  "spmv_ms": sp, "spmv_format": "3x3 BSR, fp64 values, int32 block columns",
+                  "spmv_ms": sp, "spmv_format": "3x3 blocks in SELL-32-sigma, fp64 values, int32 block columns",
                   "nnz_scalar_total": 9 * nnzb}
     peaks, peaks_src = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -365,12 +365,23 @@ def main():
             dist.destroy_process_group()
         return
 
+    # DRAM traffic per launch from the committed ncu --set full capture (same workload only)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"]["n"] == args.n and t["workload"]["n_gpus"] == world and args.model == 0:
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
     # roofline of the dominant kernel of the timed step
     dom = "element_kernel" if elem_ms >= gather_ms else "gather_blocks_kernel"
     dom_ms = max(elem_ms, gather_ms)
     ach = BYTES_PER_ELEM * cnt["local_elems"] / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
+                "frac": ach / hbm_peak, "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
                 "algorithmic_bytes_per_element": BYTES_PER_ELEM, "kernel_ms": dom_ms,
                 "phase_ms": {"element": elem_ms, "gather_k": gather_ms, "gather_r": gres_ms, "bc": bc_ms}}
     asm_ms = elem_ms + gather_ms + gres_ms
@@ -390,8 +401,8 @@ def main():
     if newton:
         line["newton"] = newton
         sp_ach = (76.0 * cnt["nnzb"] + 60.0 * cnt["owned_nodes"]) / (newton["spmv_ms"] * 1e-3) / 1e9
-        line["roofline_spmv"] = {"bound": "hbm", "kernel": "spmv_bsr_kernel", "achieved": sp_ach, "peak": hbm_peak,
-                                 "unit": "GB/s", "frac": sp_ach / hbm_peak, "traffic": None,
+        line["roofline_spmv"] = {"bound": "hbm", "kernel": "spmv_sell_kernel", "achieved": sp_ach, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": sp_ach / hbm_peak, "traffic": traffic.get("spmv_sell_kernel"),
                                  "algorithmic_bytes": "76*nnzb + 20*n (BSR form of SURVEY 8d)",
                                  "kernel_ms": newton["spmv_ms"], "timed": "CUDA events around every in-solve SpMV launch"}
 

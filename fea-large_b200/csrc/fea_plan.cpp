@@ -11,6 +11,9 @@
 //    element-major accumulation, fea_solver.c:878-882).
 #include "fea_plan.hpp"
 
+#include <omp.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -95,8 +98,19 @@ static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nran
   }
 }
 
+// Launchers export OMP_NUM_THREADS=1 for every rank (torchrun does); the planner is a one-off
+// host phase, so it takes its fair share of the cores this process may run on instead.
+static int plan_threads(int nranks) {
+  cpu_set_t set;
+  int cores = 1;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+  if (const char *s = getenv("FEA_PLAN_THREADS")) return std::max(1, atoi(s));
+  return std::max(1, std::min(32, cores / std::max(1, nranks)));
+}
+
 void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
                 const int32_t *conn, int rank, int nranks) {
+  omp_set_num_threads(plan_threads(nranks));
   if (n_nodes <= 0 || n_elems <= 0 || !X0 || !conn) throw std::runtime_error("empty mesh");
   if (rank < 0 || nranks < 1 || rank >= nranks) throw std::runtime_error("bad rank/nranks");
   for (int64_t k = 0; k < (int64_t)n_elems * NEN; ++k)

@@ -435,6 +435,18 @@ __global__ void pack_kernel(int n_nodes, const int32_t *__restrict__ nodes, cons
   if (t < 3 * n_nodes) buf[t] = v[3 * (size_t)nodes[t / 3] + t % 3];
 }
 
+// dst[l] = src[idx[l]] / dst[idx[l]] = src[l] for 3-vectors per node (host <-> local numbering)
+__global__ void gather_nodes_kernel(int n_nodes, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                                    double *__restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * n_nodes) dst[t] = src[3 * (size_t)idx[t / 3] + t % 3];
+}
+__global__ void scatter_nodes_kernel(int n_nodes, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                                     double *__restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * n_nodes) dst[3 * (size_t)idx[t / 3] + t % 3] = src[t];
+}
+
 // [ng*9][ne_pad] -> [n_elems][ng][9] for elements flagged in `take`, scattered to global ids
 __global__ void state_export_kernel(int n_elems, int ne_pad, int ng, const double *__restrict__ soa,
                                     double *__restrict__ aos) {

@@ -175,7 +175,7 @@ int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);
 int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs);
 /* tuning knobs: "pcg_batch" (iterations
  * queued between host convergence checks), "pcg_stall" (iterations without a new best
- * ||r|| before PCG declares the rounding floor; 0 = automatic, max(200, 10 n^(1/3))) */
+ * ||r|| before PCG declares the rounding floor; 0 = automatic, max(500, 50 n^(1/3))) */
 int fea_gpu_set_param(fea_gpu_handle h, const char *name, double value);
 /* overwrite >= `bytes` of scratch so L2 holds none of the caller's data */
 int fea_gpu_flush_l2(fea_gpu_handle h);

@@ -28,7 +28,8 @@ def main():
     box = [fg.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
 
-    m = block_model((4, 4 * world + 1, 4), model=1, bc_style=1, dy=0.02)
+    ny = 4 * world + 1
+    m = block_model((4, ny, 4), model=1, bc_style=1, dy=0.02, box=(1.0, ny / 4.0, 1.0))   # cubic cells of 0.25
     rng = np.random.default_rng(3)
     x0 = m.nodes + 0.004 * rng.standard_normal(m.nodes.shape)
     g = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals,
@@ -51,6 +52,11 @@ def main():
     Ssum = np.zeros_like(S)
     import torch
     t = torch.from_numpy(S.copy()); dist.all_reduce(t); Ssum = t.numpy()   # each element owned once
+    # host-buffer step on every rank (each fills its owned rows of the shared-shape host array)
+    xh, Rh = fg.host_array(m.nodes.shape), fg.host_array(m.n_dof)
+    xh[:] = x1; Rh[:] = 0.0
+    g.step_from_host(xh, Rh, True)
+    t = torch.from_numpy(np.array(Rh)); dist.all_reduce(t); R_host = t.numpy()
     status = {"ok": True}
     if rank == 0:
         s1 = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals, device=local)
@@ -64,6 +70,8 @@ def main():
         e["x1"] = relmax(x1 - m.nodes, s1.get_nodes() - m.nodes)
         e["R1"] = relmax(R1, s1.get_forces())
         e["S"] = relmax(Ssum, s1.get_state()[1])
+        s1.apply_bc(0.0)
+        e["R_hostpath"] = relmax(R_host, s1.get_forces())
         o = PortOracle(m)
         o.set_nodes(x0); o.apply_increment(1.0); o.update_state(); o.assemble_stiffness(); o.assemble_residual()
         e["R0_oracle"] = relmax(R0, o.get_forces())
@@ -71,7 +79,7 @@ def main():
         e["u_oracle"] = relmax(u, o.get_solution())
         print("MULTIRANK", world, "ranks, pcg its", it, it1, "errors", {k: f"{v:.2e}" for k, v in e.items()}, flush=True)
         good = ok and ok1 and e["R0"] < 1e-12 and e["R1"] < 1e-9 and e["u"] < 1e-9 and e["x1"] < 1e-9 \
-            and e["S"] < 1e-9 and e["R0_oracle"] < 1e-12 and e["u_oracle"] < 1e-9 and e["tol"] < 1e-9
+            and e["S"] < 1e-9 and e["R0_oracle"] < 1e-12 and e["u_oracle"] < 1e-9 and e["tol"] < 1e-9 and e["R_hostpath"] < 1e-9
         status["ok"] = bool(good)
         print("MULTIRANK_RESULT", "PASS" if good else "FAIL", flush=True)
     dist.barrier()

@@ -91,6 +91,24 @@ def test_fused_pass_equals_phase_calls(brick):
     assert all(np.array_equal(p, q) for p, q in zip(a.get_state(), b.get_state()))
 
 
+def test_host_buffer_step_equals_phase_calls(brick):
+    """fea_gpu_step_from_host (host nodes in, host residual out, BC fused into the gather) must give
+    exactly what assemble_all + apply_bc(0) give -- with pinned and with ordinary host arrays."""
+    name, m, _ = brick
+    a, b = make_gpu(m), make_gpu(m)
+    x = deformed(m, 4)
+    a.set_nodes(x); a.assemble_all(True); a.apply_bc(0.0)
+    for pinned in (False, True):
+        xh = fg.host_array(x.shape) if pinned else np.empty_like(x)
+        Rh = fg.host_array(m.n_dof) if pinned else np.empty(m.n_dof)
+        xh[:] = x; Rh[:] = np.nan
+        h2d, d2h = b.step_from_host(xh, Rh, True)
+        assert h2d == 24 * len(m.nodes) and d2h == 24 * len(m.nodes)
+        assert np.array_equal(Rh, a.get_forces())
+        assert np.array_equal(b.get_csr()[3], a.get_csr()[3])
+        assert np.array_equal(b.get_nodes(), x)
+
+
 def test_assembly_is_bit_reproducible():
     m, _ = load_golden("a5_brick")
     g = make_gpu(m)
