@@ -329,7 +329,7 @@ def main():
     newton = None
     if not args.no_newton:
         g.set_nodes(nodes)
-        its, nt_ms, relres, spmv_ms = [], [], [], []
+        its, nt_ms, relres, spmv_ms, exits = [], [], [], [], []
         for k in range(args.newton_iters):
             barrier()
             g.sync()
@@ -343,7 +343,7 @@ def main():
             g.update_nodes()
             t_ms = allmax(g.timer_stop())
             p = g.phase_ms()
-            its.append(it); nt_ms.append(t_ms); relres.append(rr); spmv_ms.append(p["spmv_avg"])
+            its.append(it); nt_ms.append(t_ms); relres.append(rr); spmv_ms.append(p["spmv_avg"]); exits.append(p["pcg_exit"])
             if rank == 0:
                 log(f"[bench] newton it {k}: {t_ms:.1f} ms, pcg {it} its (relres {rr:.2e}, ok={ok}), <R,u>={tol:.3e}, "
                     f"spmv {p['spmv_avg']:.3f} ms")
@@ -352,7 +352,8 @@ def main():
         sp = float(np.mean(spmv_ms))
         newton = {"newton_iters_per_sec": len(nt_ms) / (sum(nt_ms) * 1e-3), "ms_per_newton_iter": float(np.mean(nt_ms)),
                   "pcg_iters_per_newton_iter": float(np.mean(its)), "pcg_relres": float(max(relres)),
-                  "pcg_tol": args.lin_tol, "pcg_iters_per_sec": float(sum(its) / (sum(nt_ms) * 1e-3)),
+                  "pcg_tol": args.lin_tol, "pcg_exit": exits, "pcg_exit_legend": "1 = tolerance met, 2 = stall/divergence guard, 0 = max_iter",
+                  "pcg_iters_per_sec": float(sum(its) / (sum(nt_ms) * 1e-3)),
                   "spmv_ms": sp, "spmv_format": "3x3 blocks in SELL-32-sigma, fp64 values, int32 block columns",
                   "nnz_scalar_total": 9 * nnzb}
     peaks, peaks_src = measured_peaks()

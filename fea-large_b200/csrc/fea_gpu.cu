@@ -785,7 +785,7 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
     CU(cudaStreamSynchronize(c->stream));
     done = c->ctl_host->done || launched >= max_iter;
   }
-  double rr_final = c->ctl_host->rr;
+  double rr_final = c->ctl_host->rr_exit;
   if (c->ctl_host->done == 2) {   // stalled or diverged: the checkpoint is the answer (see pcg_step_control)
     CU(cudaMemcpyAsync(c->u, c->u_saved, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     rr_final = c->ctl_host->rr_saved;
@@ -1011,6 +1011,13 @@ extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
   out[PH_SPMV] = c->sp_used ? sp / c->sp_used : 0.0;  // average ms per in-solve SpMV launch
   out[8] = c->sp_used;
   out[9] = c->last_iters;
+  if (c->ctl_host) {   // exit state of the last solve
+    const double bb = c->ctl_host->bb > 0.0 ? c->ctl_host->bb : 1.0;
+    out[10] = c->ctl_host->done;                          // 0 = max_iter, 1 = tolerance, 2 = stall / divergence guard
+    out[11] = std::sqrt(c->ctl_host->best_rr / bb);       // best relative residual seen
+    out[12] = std::sqrt(c->ctl_host->rr_exit / bb);       // relative residual of the last iterate
+    out[13] = c->ctl_host->stall;
+  }
   return FEA_GPU_OK;
 }
 

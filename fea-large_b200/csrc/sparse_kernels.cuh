@@ -232,6 +232,8 @@ struct PcgCtl {
   double beta;
   double best_rr;   // smallest r.r seen so far (stagnation guard)
   double rr_saved;  // r.r of the checkpointed iterate (u_saved)
+  double rr_exit;   // r.r latched when `done` was set: with several ranks the queued no-op iterations
+                    // that follow keep all-reducing pq / rz_new / rr, which are garbage from then on
   int save;         // this iteration's direction kernel must checkpoint u
   int done;         // 1 = tolerance met, 2 = stalled or diverged: the checkpoint is the answer
   int iters;
@@ -311,6 +313,7 @@ pcg_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ 
     ctl->stall = 0;
     ctl->best_rr = s[2];
     ctl->rr_saved = s[2];
+    ctl->rr_exit = s[2];
     ctl->save = 0;
     if (finalize) {
       ctl->thresh = abs_tol ? tol * tol : tol * tol * s[1];
@@ -324,6 +327,7 @@ __global__ void pcg_init_finalize_kernel(PcgCtl *ctl, double tol, int abs_tol) {
   ctl->rz_old = ctl->rz_new;
   ctl->best_rr = ctl->rr;
   ctl->rr_saved = ctl->rr;
+  ctl->rr_exit = ctl->rr;
   ctl->save = 0;
   ctl->thresh = abs_tol ? tol * tol : tol * tol * ctl->bb;
   ctl->done = (ctl->bb == 0.0 || ctl->rr <= ctl->thresh) ? 1 : 0;
@@ -342,6 +346,7 @@ __device__ __forceinline__ void pcg_step_control(PcgCtl *ctl) {
   ctl->rz_old = ctl->rz_new;
   ctl->iters += 1;
   ctl->save = 0;
+  ctl->rr_exit = ctl->rr;
   if (ctl->rr <= ctl->thresh) {
     ctl->done = 1;
     return;

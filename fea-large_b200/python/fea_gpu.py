@@ -332,6 +332,8 @@ class FeaGpu:
         d = dict(zip(keys, (float(v) for v in out)))
         d["spmv_samples"] = int(out[8])
         d["pcg_iters"] = int(out[9])
+        d["pcg_exit"] = int(out[10])
+        d["pcg_best_relres"], d["pcg_last_relres"], d["pcg_stall"] = float(out[11]), float(out[12]), int(out[13])
         return d
 
     def set_param(self, name, value):

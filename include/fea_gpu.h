@@ -167,7 +167,9 @@ int fea_gpu_timer_stop(fea_gpu_handle h, double *ms);
 int fea_gpu_sync(fea_gpu_handle h);
 /* per-phase device time of the most recent call of each phase, ms:
  * [0]=element kernel, [1]=matrix gather, [2]=residual gather, [3]=bc,
- * [4]=pcg total, [5]=spmv (sum over iterations of the last solve), [6]=halo */
+ * [4]=pcg total, [5]=average in-solve spmv launch, [6]=halo, [8]=spmv launches timed,
+ * [9]=pcg iterations, [10]=pcg exit (0 max_iter, 1 tolerance, 2 stall/divergence guard),
+ * [11]=best relative residual seen, [12]=relative residual of the last iterate, [13]=stall count */
 int fea_gpu_phase_ms(fea_gpu_handle h, double out[16]);
 /* repeated SpMV on device vectors for roofline measurement: average ms per SpMV */
 int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);

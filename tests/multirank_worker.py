@@ -42,6 +42,7 @@ def main():
     R0 = g.get_forces()                      # collective all-gather
     g.apply_bc(0.0)
     it, rr, ok = g.solve(1e-13, 20000)
+    assert ok and rr <= 1e-13, (it, rr)          # the reported residual must be the converged one on every rank
     tol = g.dot_R_u()
     u = g.get_solution()
     g.update_nodes()                         # x += u, then halo exchange of x
