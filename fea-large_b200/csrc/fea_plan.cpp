@@ -565,7 +565,11 @@ extern "C" int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, dou
         for (int64_t jx = 0; jx < px; ++jx, ++k) {
           presc_node[k] = nid(jx, jy, jz);
           int type = bc_style == 1 ? 7 : 2;
-          if (bc_style == 0 && side == 0 && jx == 0 && jz == 0) type = 7;  // pin one corner
+          if (bc_style != 1 && side == 0 && jx == 0 && jz == 0) type = 7;  // pin one corner
+          // style 2: also hold the next bottom corner along x in z -- removes the free rotation about
+          // y that style 0 (the reference's "analytical" files) leaves in K, and is still satisfied by
+          // the homogeneous uniaxial state
+          if (bc_style == 2 && side == 0 && jx == px - 1 && jz == 0) type = 6;
           presc_type[k] = type;
           presc_vals[3 * k + 0] = 0.0;
           presc_vals[3 * k + 1] = side ? dy : 0.0;

@@ -213,7 +213,9 @@ int fea_plan_sell_arrays(fea_plan_handle p, int32_t *slice_ptr, int32_t *sell_ro
 /* Kuhn (Freudenthal) 6-tet block, 10-node tets in the reference node order:
  * nx*ny*nz cubes on [0,lx]x[y0,y0+ly]x[0,lz]; nodes (2nx+1)(2ny+1)(2nz+1), tets 6*nx*ny*nz.
  * Call with NULL arrays for sizes.  bc_style 0 = "analytical" (face y=y0: type 2 value 0
- * plus one corner type 7; face y=y0+ly: type 2 value dy), 1 = clamped (type 7 on both). */
+ * plus one corner type 7; face y=y0+ly: type 2 value dy -- K keeps a free rotation about y, as in
+ * the reference's *_analytical.sexp), 1 = clamped (type 7 on both), 2 = style 0 plus a second bottom
+ * corner held in z (no rigid mode left; the homogeneous uniaxial state is still the solution). */
 int fea_mesh_block(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz,
                    double y0, int32_t bc_style, double dy, int64_t *n_nodes,
                    int64_t *n_elems, int64_t *n_presc, double *nodes, int32_t *conn,
