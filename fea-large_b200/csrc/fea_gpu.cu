@@ -864,8 +864,12 @@ extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, 
                                int32_t *colidx, double *vals) {
   CHECK_H(c);
   const fea::Plan &pl = c->plan;
+  // a node that belongs to no element carries an internal lone diagonal block (so Jacobi has a
+  // diagonal to invert); the reference's container has no entry there, so the export hides it
+  int64_t isolated = 0;
+  for (int32_t l = 0; l < c->n_own; ++l) isolated += pl.rptr[(size_t)l + 1] == pl.rptr[(size_t)l];
   if (n_rows) *n_rows = 3 * (int64_t)c->n_own;
-  if (nnz) *nnz = 9 * c->nnzb;
+  if (nnz) *nnz = 9 * (c->nnzb - isolated);
   // rows are returned in ascending GLOBAL id (the device keeps them in Morton / SELL order)
   std::vector<int32_t> by_gid((size_t)c->n_own);
   for (int32_t l = 0; l < c->n_own; ++l) by_gid[(size_t)l] = l;
@@ -891,7 +895,8 @@ extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, 
     const int64_t sbase = pl.slice_ptr[(size_t)(rl / fea::SELL_C)];
     const int lane = rl % fea::SELL_C;
     order.clear();
-    for (int32_t q = b0; q < b1; ++q) order.emplace_back(pl.node_gid[(size_t)pl.bcol[(size_t)q]], q - b0);
+    if (pl.rptr[(size_t)l + 1] != pl.rptr[(size_t)l])
+      for (int32_t q = b0; q < b1; ++q) order.emplace_back(pl.node_gid[(size_t)pl.bcol[(size_t)q]], q - b0);
     std::sort(order.begin(), order.end());
     for (int i = 0; i < 3; ++i) {
       if (rowptr) rowptr[3 * (size_t)k + i] = (int32_t)out;
