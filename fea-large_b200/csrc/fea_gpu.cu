@@ -112,12 +112,12 @@ struct fea_gpu_ctx {
   int32_t *io_idx = nullptr, *own_idx = nullptr;   // local node -> offset inside the range
   double *io_buf = nullptr;
 
-  cudaEvent_t ev_a[PH_COUNT], ev_b[PH_COUNT];
-  bool ev_set[PH_COUNT];
-  cudaEvent_t sp_a[SPMV_EVENT_POOL], sp_b[SPMV_EVENT_POOL];
+  cudaEvent_t ev_a[PH_COUNT] = {}, ev_b[PH_COUNT] = {};
+  bool ev_set[PH_COUNT] = {};
+  cudaEvent_t sp_a[SPMV_EVENT_POOL] = {}, sp_b[SPMV_EVENT_POOL] = {};
   int sp_used = 0;
   int last_iters = 0;
-  cudaEvent_t tm_a, tm_b;
+  cudaEvent_t tm_a = nullptr, tm_b = nullptr;
   std::vector<int32_t> own_count;  // owned nodes per rank
 };
 
@@ -450,6 +450,16 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->stage_h) cudaFreeHost(c->stage_h);
+  for (int i = 0; i < PH_COUNT; ++i) {
+    if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]);
+    if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]);
+  }
+  for (int i = 0; i < SPMV_EVENT_POOL; ++i) {
+    if (c->sp_a[i]) cudaEventDestroy(c->sp_a[i]);
+    if (c->sp_b[i]) cudaEventDestroy(c->sp_b[i]);
+  }
+  if (c->tm_a) cudaEventDestroy(c->tm_a);
+  if (c->tm_b) cudaEventDestroy(c->tm_b);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return FEA_GPU_OK;
@@ -482,21 +492,26 @@ static int gather_owned(fea_gpu_ctx *c, const double *dev_vec, double *host_glob
   for (int32_t v : c->own_count) maxown = std::max(maxown, v);
   const size_t blk = 3 * (size_t)maxown;
   double *sbuf = nullptr, *rbuf = nullptr;
-  TRY(dev_alloc(&sbuf, blk));
-  TRY(dev_alloc(&rbuf, blk * (size_t)pl.nranks));
-  CU(cudaMemsetAsync(sbuf, 0, sizeof(double) * blk, c->stream));
-  CU(cudaMemcpyAsync(sbuf, dev_vec, sizeof(double) * 3 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
-  NC(ncclAllGather(sbuf, rbuf, blk, ncclDouble, c->comm, c->stream));
   std::vector<double> tmp(blk * (size_t)pl.nranks);
-  CU(cudaMemcpyAsync(tmp.data(), rbuf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  auto body = [&]() -> int {
+    TRY(dev_alloc(&sbuf, blk));
+    TRY(dev_alloc(&rbuf, blk * (size_t)pl.nranks));
+    CU(cudaMemsetAsync(sbuf, 0, sizeof(double) * blk, c->stream));
+    CU(cudaMemcpyAsync(sbuf, dev_vec, sizeof(double) * 3 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
+    NC(ncclAllGather(sbuf, rbuf, blk, ncclDouble, c->comm, c->stream));
+    CU(cudaMemcpyAsync(tmp.data(), rbuf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FEA_GPU_OK;
+  };
+  const int rc = body();
+  cudaFree(sbuf);
+  cudaFree(rbuf);
+  if (rc != FEA_GPU_OK) return rc;
   for (int64_t g = 0; g < pl.n_nodes_global; ++g) {  // every rank knows every owner's numbering
     const int o = pl.owner[(size_t)g];
     std::memcpy(host_global + 3 * (size_t)g, tmp.data() + blk * (size_t)o + 3 * (size_t)pl.pos_in_owner[(size_t)g],
                 3 * sizeof(double));
   }
-  cudaFree(sbuf);
-  cudaFree(rbuf);
   return FEA_GPU_OK;
 }
 
