@@ -13,8 +13,9 @@
 // Mapping: a CTA handles 32 elements with NG warps; warp w owns Gauss point w, lane l owns
 // element l.  Phase A (one thread per (element, Gauss point)) keeps everything in
 // registers; its results cross to phase B through shared memory laid out
-// [gauss][field][lane] (conflict-free, lane-contiguous).  Phase B gives every thread 55/NG
-// of the a<=b node-pair blocks of its lane's element and loops over the Gauss points.
+// [gauss][field][lane] in 16-byte fields (conflict-free LDS.128/STS.128).  Phase B gives warp
+// w the eleven a<=b blocks of staging region w (rows w and 9-w, fea_plan.hpp) of its lane's
+// element, two consecutive blocks at a time, summed over the Gauss points.
 //
 // Closed form used for the tangent (both models):
 //   c^_ikjl = lam' d_ik d_jl + mu' (d_ij d_kl + d_il d_jk)
@@ -24,11 +25,14 @@
 #pragma once
 #include <cstdint>
 
+#include "fea_plan.hpp"
+
 namespace fea {
 
 constexpr int ELEMS_PER_CTA = 32;
-constexpr int NFIELD = 62;  // g[3][10], t[3][10], lam', mu'
-constexpr int TILE_LD = 19;  // per-lane pitch of the store-transpose tile (odd: conflict-free)
+// 16-byte fields per Gauss point: node b -> (g0,g1), (g2,t0), (t1,t2); field 30 -> (lam' wd, mu' wd)
+constexpr int NF2 = 31;
+constexpr int TILE_D2 = 9 * 32;  // double2 per warp: the store-transpose tile of one block pair
 
 struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
@@ -45,7 +49,7 @@ struct ElemArgs {
   double lambda, mu;
   double *F_soa;               // [ng*9][ne_pad]   (may be null)
   double *S_soa;               // [ng*9][ne_pad]
-  double *Ke;                  // [n_elems][55][9]  upper-triangular node-pair blocks
+  double *Ke;                  // [n_elems][KE_STRIDE]  a<=b node-pair blocks, layout in fea_plan.hpp
   double *Re;                  // [30][ne_pad]
   unsigned long long *bad;     // count of points with det J <= 0, det F <= 0 or non-finite
 };
@@ -72,17 +76,20 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
 
 template <int MODEL, int NG, bool WITH_K, bool WITH_R>
 __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
-  extern __shared__ double sm[];  // [NG][NFIELD][32] fields, then [NG][32][TILE_LD] store tiles
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double2 *fld = reinterpret_cast<double2 *>(smraw);  // [NG][NF2][32] fields
+  double2 *tiles = fld + NG * NF2 * 32;               // [NG][TILE_D2] store tiles
   const int lane = threadIdx.x & 31;
   const int gp = threadIdx.x >> 5;
-  const int e = blockIdx.x * ELEMS_PER_CTA + lane;
+  const int e0 = blockIdx.x * ELEMS_PER_CTA;
+  const int e = e0 + lane;
   const bool live = e < A.n_elems;
-  double *my = sm + (size_t)gp * NFIELD * 32 + lane;  // field f at my[f*32]
+  double2 *my = fld + gp * NF2 * 32 + lane;  // field f at my[f*32]
 
   // ------------------------------ phase 0 ------------------------------------
   // the NG warps of the CTA fetch the 10 nodes of the 32 elements once (coalesced connectivity,
   // gathered coordinates) into the region the store tiles will use later: [node][x0..2,X0..2][lane]
-  double *coords = sm + (size_t)NG * NFIELD * 32;
+  double *coords = reinterpret_cast<double *>(tiles);
   for (int a = gp; a < 10; a += NG) {
     const int node = live ? A.conn_soa[(size_t)a * A.ne_pad + e] : 0;
     const double *xk = A.x + 3 * (size_t)node, *Xk = A.X0 + 3 * (size_t)node;
@@ -206,108 +213,153 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     const double lw = lam1 * wd, mw = mu1 * wd;
 #pragma unroll
     for (int a = 0; a < 10; ++a) {
+      double gg[3], tt[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const double sg = S[i][0] * g[0][a] + S[i][1] * g[1][a] + S[i][2] * g[2][a];
-        my[(i * 10 + a) * 32] = ok ? g[i][a] : 0.0;
-        my[(30 + i * 10 + a) * 32] = ok ? fma(wd, sg, mw * g[i][a]) : 0.0;
+        gg[i] = ok ? g[i][a] : 0.0;
+        tt[i] = ok ? fma(wd, sg, mw * g[i][a]) : 0.0;
       }
+      my[(3 * a + 0) * 32] = make_double2(gg[0], gg[1]);
+      my[(3 * a + 1) * 32] = make_double2(gg[2], tt[0]);
+      my[(3 * a + 2) * 32] = make_double2(tt[1], tt[2]);
     }
-    my[60 * 32] = lw;
-    my[61 * 32] = mw;
+    my[30 * 32] = make_double2(lw, mw);
   }
   __syncthreads();
 
   // ------------------------------ phase B ------------------------------------
-  const double *col = sm + lane;  // field f of Gauss point q at col[(q*NFIELD + f)*32]
-#define FLD(q, f) col[((q)*NFIELD + (f)) * 32]
+  const double2 *col = fld + lane;  // field f of Gauss point q at col[(q*NF2 + f)*32]
+#define FLD2(q, f) col[((q)*NF2 + (f)) * 32]
 
   if (WITH_R) {
     // R_e[a][i] = -sum_g wd (sigma g_a)_i = -sum_g (t_ai - mu' g_ai)   (fea_solver.c:1094-1109)
-    for (int idx = gp; idx < 30; idx += NG) {
-      const int a = idx / 3, i = idx - 3 * a;
-      double acc = 0.0;
+    for (int a = gp; a < 10; a += NG) {
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
-      for (int q = 0; q < NG; ++q)
-        acc += FLD(q, 30 + i * 10 + a) - FLD(q, 61) * FLD(q, i * 10 + a);
-      if (live) A.Re[(size_t)idx * A.ne_pad + e] = -acc;
+      for (int q = 0; q < NG; ++q) {
+        const double2 G0 = FLD2(q, 3 * a), G1 = FLD2(q, 3 * a + 1), G2 = FLD2(q, 3 * a + 2);
+        const double mw = FLD2(q, 30).y;
+        r0 += G1.y - mw * G0.x;
+        r1 += G2.x - mw * G0.y;
+        r2 += G2.y - mw * G1.x;
+      }
+      if (live) {
+        A.Re[(size_t)(3 * a + 0) * A.ne_pad + e] = -r0;
+        A.Re[(size_t)(3 * a + 1) * A.ne_pad + e] = -r1;
+        A.Re[(size_t)(3 * a + 2) * A.ne_pad + e] = -r2;
+      }
     }
   }
 
   if (WITH_K) {
-    // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- consecutive in
-    // the packed upper triangle, i.e. 144 contiguous bytes of K_e staging -- then the warp
-    // transposes them through a padded tile so its stores walk those 144-byte chunks with
-    // consecutive lanes (8-byte stores at a 3960-byte lane stride cost 27 L2 sectors per
-    // request in v1; see profiles/r1_v1_ncu_full_summary.md).
-    double *tile = sm + (size_t)NG * NFIELD * 32 + (size_t)gp * 32 * TILE_LD;
-    const int e0 = blockIdx.x * ELEMS_PER_CTA;
-    // rows a and 9-a of the upper triangle hold 11 blocks together: one such pair per warp
-    // when NG == 5 (pairs are dealt round-robin otherwise)
+    // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- 144 contiguous,
+    // 16-byte aligned bytes of the staging -- and the warp transposes them through its tile so
+    // that the global stores are 16-byte pieces walking those 144-byte chunks with consecutive
+    // lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per request; v3
+    // transposed but spent ~25 instructions of index arithmetic per 8-byte store, see
+    // profiles/r1_v3_ncu_full_summary.md -- here the per-lane offsets are computed once.)
+    double2 *tile = tiles + gp * TILE_D2;
+    const int n_here = min(ELEMS_PER_CTA, A.n_elems - e0);
+    // piece f = 32 it + lane of the warp's [32 elements][9 double2] tile belongs to element f / 9
+    int goff[9];
+    unsigned vmask = 0;
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int f = it * 32 + lane, le = f / 9;
+      goff[it] = le * KE_STRIDE + 2 * (f - 9 * le);
+      if (le < n_here) vmask |= 1u << it;
+    }
+    double *kcta = A.Ke + (size_t)e0 * KE_STRIDE;
     for (int pr = gp; pr < 5; pr += NG)
       for (int half = 0; half < 2; ++half) {
         const int a = half ? 9 - pr : pr;
         double ga[NG][3], ua[NG][3], va[NG][3];
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-          const double lw = FLD(q, 60), mw = FLD(q, 61);
+          const double2 G0 = FLD2(q, 3 * a), G1 = FLD2(q, 3 * a + 1), LM = FLD2(q, 30);
+          ga[q][0] = G0.x;
+          ga[q][1] = G0.y;
+          ga[q][2] = G1.x;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            ga[q][i] = FLD(q, i * 10 + a);
-            ua[q][i] = lw * ga[q][i];
-            va[q][i] = mw * ga[q][i];
+            ua[q][i] = LM.x * ga[q][i];
+            va[q][i] = LM.y * ga[q][i];
           }
         }
         for (int b = a; b < 10; b += 2) {
           const bool two = b + 1 < 10;   // warp-uniform
           double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
             {
-              const double gb[3] = {FLD(q, b), FLD(q, 10 + b), FLD(q, 20 + b)};
-              const double s = ga[q][0] * FLD(q, 30 + b) + ga[q][1] * FLD(q, 40 + b) + ga[q][2] * FLD(q, 50 + b);
+              const double2 G0 = FLD2(q, 3 * b), G1 = FLD2(q, 3 * b + 1), G2 = FLD2(q, 3 * b + 2);
+              const double gb[3] = {G0.x, G0.y, G1.x};
+              s0 = fma(ga[q][0], G1.y, fma(ga[q][1], G2.x, fma(ga[q][2], G2.y, s0)));
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                   k0[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
-              k0[0] += s;
-              k0[4] += s;
-              k0[8] += s;
             }
             if (two) {
               const int b1 = b + 1;
-              const double gb[3] = {FLD(q, b1), FLD(q, 10 + b1), FLD(q, 20 + b1)};
-              const double s = ga[q][0] * FLD(q, 30 + b1) + ga[q][1] * FLD(q, 40 + b1) + ga[q][2] * FLD(q, 50 + b1);
+              const double2 G0 = FLD2(q, 3 * b1), G1 = FLD2(q, 3 * b1 + 1), G2 = FLD2(q, 3 * b1 + 2);
+              const double gb[3] = {G0.x, G0.y, G1.x};
+              s1 = fma(ga[q][0], G1.y, fma(ga[q][1], G2.x, fma(ga[q][2], G2.y, s1)));
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                   k1[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
-              k1[0] += s;
-              k1[4] += s;
-              k1[8] += s;
             }
           }
+          k0[0] += s0;
+          k0[4] += s0;
+          k0[8] += s0;
+          k1[0] += s1;
+          k1[4] += s1;
+          k1[8] += s1;
+          double *dst = kcta + 100 * pr + 9 * ke_pos(a, b);
+          if (two) {
+            double2 *t = tile + lane * 9;
+            t[0] = make_double2(k0[0], k0[1]);
+            t[1] = make_double2(k0[2], k0[3]);
+            t[2] = make_double2(k0[4], k0[5]);
+            t[3] = make_double2(k0[6], k0[7]);
+            t[4] = make_double2(k0[8], k1[0]);
+            t[5] = make_double2(k1[1], k1[2]);
+            t[6] = make_double2(k1[3], k1[4]);
+            t[7] = make_double2(k1[5], k1[6]);
+            t[8] = make_double2(k1[7], k1[8]);
+            __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 9; ++c) {
-            tile[lane * TILE_LD + c] = k0[c];
-            tile[lane * TILE_LD + 9 + c] = k1[c];
+            for (int it = 0; it < 9; ++it) {
+              const double2 v = tile[it * 32 + lane];
+              if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + goff[it]) = v;
+            }
+            __syncwarp();
+          } else {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
+            double2 *t = tile + lane * 5;
+            t[0] = make_double2(k0[0], k0[1]);
+            t[1] = make_double2(k0[2], k0[3]);
+            t[2] = make_double2(k0[4], k0[5]);
+            t[3] = make_double2(k0[6], k0[7]);
+            t[4] = make_double2(k0[8], 0.0);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+              const int f = it * 32 + lane, le = f / 5;
+              const double2 v = tile[f];
+              if (le < n_here) *reinterpret_cast<double2 *>(dst + le * KE_STRIDE + 2 * (f - 5 * le)) = v;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          const int tri = a * 10 - (a * (a - 1)) / 2 + (b - a);
-          const int nd = two ? 18 : 9;
-          for (int it = 0; it < nd; ++it) {
-            const int f = it * 32 + lane;
-            const int le = two ? f / 18 : f / 9;
-            const int cc = f - le * nd;
-            if (e0 + le < A.n_elems) A.Ke[((size_t)(e0 + le) * 55 + tri) * 9 + cc] = tile[le * TILE_LD + cc];
-          }
-          __syncwarp();
         }
       }
   }
-#undef FLD
+#undef FLD2
 }
 
 }  // namespace fea

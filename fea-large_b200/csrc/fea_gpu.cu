@@ -354,7 +354,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   const size_t n3 = 3 * (size_t)c->n_own, nl3 = 3 * (size_t)c->n_local;
   TRY(dev_alloc(&c->F_soa, (size_t)c->ng * 9 * c->ne_pad));
   TRY(dev_alloc(&c->S_soa, (size_t)c->ng * 9 * c->ne_pad));
-  TRY(dev_alloc(&c->Ke, (size_t)c->n_elems * 55 * 9));
+  TRY(dev_alloc(&c->Ke, (size_t)c->n_elems * fea::KE_STRIDE));
   TRY(dev_alloc(&c->Re, (size_t)30 * c->ne_pad));
   TRY(dev_alloc(&c->vals, (size_t)c->n_slots * 9));
   TRY(dev_alloc(&c->R, n3));
@@ -577,7 +577,7 @@ extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
 template <int MODEL, int NG>
 static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
   const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
-  const size_t smem = sizeof(double) * NG * (fea::NFIELD + fea::TILE_LD) * 32;
+  const size_t smem = sizeof(double2) * NG * (fea::NF2 * 32 + fea::TILE_D2);
 #define FEA_LAUNCH(K, Rr)                                                                          \
   do {                                                                                             \
     auto kern = fea::element_kernel<MODEL, NG, K, Rr>;                                             \

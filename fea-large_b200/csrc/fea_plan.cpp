@@ -276,7 +276,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
         const int32_t *c = &p.conn[(size_t)le * NEN];
         for (int b = 0; b < NEN; ++b) {
           int32_t pos = (int32_t)(std::lower_bound(row, row + len, c[b]) - row);
-          uint32_t src = (uint32_t)le * NTRI + (uint32_t)tri_index(std::min(a, b), std::max(a, b));
+          uint32_t src = (uint32_t)le * NTRI + (uint32_t)ke_code(std::min(a, b), std::max(a, b));
           if (a > b) src |= SRC_TRANSPOSE;   // stored block is K_e[b][a]; K_e[a][b] is its transpose
           p.csrc[(size_t)cur[(size_t)pos]++] = src;
         }

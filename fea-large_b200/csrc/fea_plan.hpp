@@ -13,8 +13,28 @@ constexpr int NEN = 10;                 // nodes per TETRAHEDRA10
 constexpr int NTRI = 55;                // upper-triangular (a<=b) node pairs per element
 constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
 
-// index of pair (a<=b) in the packed upper triangle, row-major
-inline int tri_index(int a, int b) { return a * NEN - (a * (a - 1)) / 2 + (b - a); }
+// K_e staging layout (what element_kernel writes and gather_blocks_kernel reads).  The 55 a<=b
+// blocks of an element are grouped in five regions of 11: region pr = min(a, 9-a) holds row pr
+// (10-pr blocks) and row 9-pr (pr+1 blocks) -- the work of one warp of the element kernel.  Inside
+// a region the blocks come in consecutive pairs (a,b),(a,b+1) (first row's pairs, then the second
+// row's: always five pairs) and the one block left over, (a,9) of the row with an odd count, last.
+// code = 11 pr + pos; the block lives at double offset 500 e + 100 pr + 9 pos = 9 idx + idx / 11
+// with idx = 55 e + code, so every pair starts on a 16-byte boundary (one pad double per region).
+constexpr int KE_STRIDE = 500;          // doubles per element
+#if defined(__CUDACC__)
+#define FEA_HD __host__ __device__
+#else
+#define FEA_HD
+#endif
+FEA_HD inline int ke_pos(int a, int b) {   // a <= b
+  const int pr = a < NEN - 1 - a ? a : NEN - 1 - a;
+  const int n0 = NEN - pr;                 // blocks of row pr
+  const int k = b - a;
+  if (a == pr) return k < (n0 & ~1) ? k : 10;
+  const int n1 = pr + 1;                   // blocks of row 9-pr
+  return k < (n1 & ~1) ? (n0 & ~1) + k : 10;
+}
+FEA_HD inline int ke_code(int a, int b) { return 11 * (a < NEN - 1 - a ? a : NEN - 1 - a) + ke_pos(a, b); }
 
 constexpr int SELL_C = 32;              // rows per SELL slice = one warp
 constexpr int SELL_SIGMA = 2048;        // rows per length-sorting window

@@ -117,7 +117,8 @@ gather_blocks_kernel(SellMat A, const int32_t *__restrict__ cptr, const uint32_t
       double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int k = k0; k < k1; ++k) {
         const uint32_t src = csrc[k];
-        const double *b = Ke + (size_t)(src & 0x7fffffffu) * 9;
+        const uint32_t idx = src & 0x7fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
+        const double *b = Ke + ((size_t)idx * 9 + idx / 11u);
         double v[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) v[c] = b[c];

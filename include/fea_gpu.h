@@ -196,7 +196,9 @@ int fea_plan_counts(fea_plan_handle p, int64_t out[16]);
  *   browptr         [owned nodes + 1]  block-row pointers
  *   bcol            [nnzb]             local column node ids, ascending
  *   cptr            [nnzb + 1], csrc [contributions]  gather map (ascending global element id);
- *                   csrc = elem*55 + tri(a,b) | (1<<31 if the stored block is transposed)
+ *                   csrc = elem*55 + code(a,b) | (1<<31 if the stored block is transposed);
+ *                   code = 11*min(a,9-a) + pos orders the a<=b blocks as the element kernel
+ *                   stages them (fea_plan.hpp: ke_code)
  *   nbr_rank [nbr], send_ptr [nbr+1], send_nodes [sent] (local ids), recv_ptr [nbr+1]
  *                   (ghost offset ranges, in local numbering minus owned count) */
 int fea_plan_arrays(fea_plan_handle p, int32_t *local_node_gid, int32_t *local_elem_gid,

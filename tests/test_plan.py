@@ -7,7 +7,24 @@ import fea_gpu as fg
 from conftest import block_model, csr_mv, load_golden
 from oracle.oracle import PortOracle
 
-TRI = {(a, b): a * 10 - (a * (a - 1)) // 2 + (b - a) for a in range(10) for b in range(a, 10)}
+
+
+def ke_code(a, b):
+    """Staging order of the a<=b blocks of K_e, restated from fea_plan.hpp: region pr = min(a, 9-a)
+    holds rows pr and 9-pr as five consecutive pairs, the left-over block (a,9) of the odd row last."""
+    pr = min(a, 9 - a)
+    first = list(range(pr, 10))            # columns of row pr
+    second = list(range(9 - pr, 10))       # columns of row 9-pr
+    order = []
+    for row, cols in ((pr, first), (9 - pr, second)):
+        order += [(row, c) for c in cols[:len(cols) // 2 * 2]]
+    order += [(row, 9) for row, cols in ((pr, first), (9 - pr, second)) if len(cols) % 2]
+    assert len(order) == 11
+    return 11 * pr + order.index((a, b))
+
+
+TRI = {(a, b): ke_code(a, b) for a in range(10) for b in range(a, 10)}
+assert sorted(TRI.values()) == list(range(55))
 
 
 def staged_blocks(o, n_elems):
