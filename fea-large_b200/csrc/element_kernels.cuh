@@ -30,9 +30,13 @@
 namespace fea {
 
 constexpr int ELEMS_PER_CTA = 32;
-// 16-byte fields per Gauss point: node b -> (g0,g1), (g2,t0), (t1,t2); field 30 -> (lam' wd, mu' wd)
-constexpr int NF2 = 31;
-constexpr int TILE_D2 = 9 * 32;  // double2 per warp: the store-transpose tile of one block pair
+// Hand-over fields per Gauss point, [field][lane] (lane-contiguous: conflict-free):
+//   double2 GA[b] = (g0,g1) and TA[b] = (t0,t1) for the 10 nodes, double2 LM = (lam' wd, mu' wd),
+//   then plain doubles g2[b], t2[b].  g = grad N_b, t = (mu' wd I + wd sigma) g.
+// The column side of a block needs only g (24 bytes per Gauss point), the row side g and t.
+constexpr int FLD_DOUBLES = 62 * 32;          // doubles per Gauss point
+constexpr int FLD_TA = 10 * 64, FLD_LM = 20 * 64, FLD_G2 = 21 * 64, FLD_T2 = 21 * 64 + 10 * 32;
+constexpr int TILE_D2 = 9 * 32;               // double2 per warp: the store-transpose tile of one block pair
 
 struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
@@ -77,14 +81,14 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
 template <int MODEL, int NG, bool WITH_K, bool WITH_R>
 __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  double2 *fld = reinterpret_cast<double2 *>(smraw);  // [NG][NF2][32] fields
-  double2 *tiles = fld + NG * NF2 * 32;               // [NG][TILE_D2] store tiles
+  double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
+  double2 *tiles = reinterpret_cast<double2 *>(fld + NG * FLD_DOUBLES);  // [NG][TILE_D2] store tiles
+  int *goff = reinterpret_cast<int *>(tiles + NG * TILE_D2);             // [9][32] store offsets
   const int lane = threadIdx.x & 31;
   const int gp = threadIdx.x >> 5;
   const int e0 = blockIdx.x * ELEMS_PER_CTA;
   const int e = e0 + lane;
   const bool live = e < A.n_elems;
-  double2 *my = fld + gp * NF2 * 32 + lane;  // field f at my[f*32]
 
   // ------------------------------ phase 0 ------------------------------------
   // the NG warps of the CTA fetch the 10 nodes of the 32 elements once (coalesced connectivity,
@@ -97,6 +101,15 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     for (int d = 0; d < 3; ++d) {
       coords[((a * 6 + d) * 32) + lane] = xk[d];
       coords[((a * 6 + 3 + d) * 32) + lane] = Xk[d];
+    }
+  }
+  if (WITH_K && gp == 0) {
+    // where the 16-byte pieces of a block pair go: piece f = 32 it + lane of a warp's
+    // [32 elements][9 double2] tile belongs to element f / 9 (same table for every warp and pair)
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int f = it * 32 + lane, le = f / 9;
+      goff[f] = le * KE_STRIDE + 2 * (f - 9 * le);
     }
   }
   __syncthreads();
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     // hand over to phase B: g, t = (mu' I + sigma) g scaled by wd, and the scaled coefficients
     const double wd = ok ? c_tab.w[gp] * fabs(detJ) : 0.0;  // fabs: fea_solver.c:958,1047,1104
     const double lw = lam1 * wd, mw = mu1 * wd;
+    double *my = fld + gp * FLD_DOUBLES;
 #pragma unroll
     for (int a = 0; a < 10; ++a) {
       double gg[3], tt[3];
@@ -220,73 +234,73 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         gg[i] = ok ? g[i][a] : 0.0;
         tt[i] = ok ? fma(wd, sg, mw * g[i][a]) : 0.0;
       }
-      my[(3 * a + 0) * 32] = make_double2(gg[0], gg[1]);
-      my[(3 * a + 1) * 32] = make_double2(gg[2], tt[0]);
-      my[(3 * a + 2) * 32] = make_double2(tt[1], tt[2]);
+      reinterpret_cast<double2 *>(my + a * 64)[lane] = make_double2(gg[0], gg[1]);
+      reinterpret_cast<double2 *>(my + FLD_TA + a * 64)[lane] = make_double2(tt[0], tt[1]);
+      my[FLD_G2 + a * 32 + lane] = gg[2];
+      my[FLD_T2 + a * 32 + lane] = tt[2];
     }
-    my[30 * 32] = make_double2(lw, mw);
+    reinterpret_cast<double2 *>(my + FLD_LM)[lane] = make_double2(lw, mw);
   }
   __syncthreads();
 
   // ------------------------------ phase B ------------------------------------
-  const double2 *col = fld + lane;  // field f of Gauss point q at col[(q*NF2 + f)*32]
-#define FLD2(q, f) col[((q)*NF2 + (f)) * 32]
+  // Warp w takes staging region w (fea_plan.hpp): rows w and 9-w of the a<=b block triangle, eleven
+  // blocks, two consecutive ones at a time.  With t symmetric in sigma, g_a . t_b = t_a . g_b, so
+  //   K_ab[i][j] = sum_q  u_ai g_bj + v_aj g_bi + d_ij t_a . g_b,   u = lam' wd g_a, v = mu' wd g_a
+  // and the column side streams 24 bytes per Gauss point from shared memory; u, v, t of the row stay
+  // in registers.  The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of
+  // the same loads.
+#define GA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + (b)*64)[lane]
+#define TA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_TA + (b)*64)[lane]
+#define LM2(q) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_LM)[lane]
+#define G2D(q, b) fld[(q)*FLD_DOUBLES + FLD_G2 + (b)*32 + lane]
+#define T2D(q, b) fld[(q)*FLD_DOUBLES + FLD_T2 + (b)*32 + lane]
 
-  if (WITH_R) {
-    // R_e[a][i] = -sum_g wd (sigma g_a)_i = -sum_g (t_ai - mu' g_ai)   (fea_solver.c:1094-1109)
-    for (int a = gp; a < 10; a += NG) {
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-#pragma unroll
-      for (int q = 0; q < NG; ++q) {
-        const double2 G0 = FLD2(q, 3 * a), G1 = FLD2(q, 3 * a + 1), G2 = FLD2(q, 3 * a + 2);
-        const double mw = FLD2(q, 30).y;
-        r0 += G1.y - mw * G0.x;
-        r1 += G2.x - mw * G0.y;
-        r2 += G2.y - mw * G1.x;
-      }
-      if (live) {
-        A.Re[(size_t)(3 * a + 0) * A.ne_pad + e] = -r0;
-        A.Re[(size_t)(3 * a + 1) * A.ne_pad + e] = -r1;
-        A.Re[(size_t)(3 * a + 2) * A.ne_pad + e] = -r2;
-      }
-    }
-  }
-
-  if (WITH_K) {
-    // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- 144 contiguous,
-    // 16-byte aligned bytes of the staging -- and the warp transposes them through its tile so
-    // that the global stores are 16-byte pieces walking those 144-byte chunks with consecutive
-    // lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per request; v3
-    // transposed but spent ~25 instructions of index arithmetic per 8-byte store, see
-    // profiles/r1_v3_ncu_full_summary.md -- here the per-lane offsets are computed once.)
+  if (WITH_K || WITH_R) {
     double2 *tile = tiles + gp * TILE_D2;
     const int n_here = min(ELEMS_PER_CTA, A.n_elems - e0);
-    // piece f = 32 it + lane of the warp's [32 elements][9 double2] tile belongs to element f / 9
-    int goff[9];
-    unsigned vmask = 0;
+    unsigned vmask = 0;   // bit it: piece 32 it + lane belongs to an element that exists
 #pragma unroll
-    for (int it = 0; it < 9; ++it) {
-      const int f = it * 32 + lane, le = f / 9;
-      goff[it] = le * KE_STRIDE + 2 * (f - 9 * le);
-      if (le < n_here) vmask |= 1u << it;
-    }
+    for (int it = 0; it < 9; ++it)
+      if ((it * 32 + lane) / 9 < n_here) vmask |= 1u << it;
     double *kcta = A.Ke + (size_t)e0 * KE_STRIDE;
     for (int pr = gp; pr < 5; pr += NG)
       for (int half = 0; half < 2; ++half) {
         const int a = half ? 9 - pr : pr;
-        double ga[NG][3], ua[NG][3], va[NG][3];
+        double ua[NG][3], va[NG][3], ta[NG][3];
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-          const double2 G0 = FLD2(q, 3 * a), G1 = FLD2(q, 3 * a + 1), LM = FLD2(q, 30);
-          ga[q][0] = G0.x;
-          ga[q][1] = G0.y;
-          ga[q][2] = G1.x;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            ua[q][i] = LM.x * ga[q][i];
-            va[q][i] = LM.y * ga[q][i];
+          const double2 G = GA2(q, a), T = TA2(q, a), LM = LM2(q);
+          const double g2 = G2D(q, a);
+          ta[q][0] = T.x;
+          ta[q][1] = T.y;
+          ta[q][2] = T2D(q, a);
+          ua[q][0] = LM.x * G.x;
+          ua[q][1] = LM.x * G.y;
+          ua[q][2] = LM.x * g2;
+          // explicitly rounded: the residual must not depend on whether K is built in the same pass
+          va[q][0] = __dmul_rn(LM.y, G.x);
+          va[q][1] = __dmul_rn(LM.y, G.y);
+          va[q][2] = __dmul_rn(LM.y, g2);
+          if (WITH_R) {
+            r0 = __dadd_rn(r0, __dsub_rn(ta[q][0], va[q][0]));
+            r1 = __dadd_rn(r1, __dsub_rn(ta[q][1], va[q][1]));
+            r2 = __dadd_rn(r2, __dsub_rn(ta[q][2], va[q][2]));
           }
         }
+        if (WITH_R && live) {
+          A.Re[(size_t)(3 * a + 0) * A.ne_pad + e] = -r0;
+          A.Re[(size_t)(3 * a + 1) * A.ne_pad + e] = -r1;
+          A.Re[(size_t)(3 * a + 2) * A.ne_pad + e] = -r2;
+        }
+        if (!WITH_K) continue;
+        // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- 144 contiguous,
+        // 16-byte aligned bytes of the staging -- and the warp transposes them through its tile so
+        // that the global stores are 16-byte pieces walking those 144-byte chunks with consecutive
+        // lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per request; v3
+        // transposed but spent ~25 instructions of index arithmetic per 8-byte store,
+        // profiles/r1_v3_ncu_full_summary.md -- here the per-lane offsets come from a table.)
         for (int b = a; b < 10; b += 2) {
           const bool two = b + 1 < 10;   // warp-uniform
           double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -294,9 +308,9 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
             {
-              const double2 G0 = FLD2(q, 3 * b), G1 = FLD2(q, 3 * b + 1), G2 = FLD2(q, 3 * b + 2);
-              const double gb[3] = {G0.x, G0.y, G1.x};
-              s0 = fma(ga[q][0], G1.y, fma(ga[q][1], G2.x, fma(ga[q][2], G2.y, s0)));
+              const double2 G = GA2(q, b);
+              const double gb[3] = {G.x, G.y, G2D(q, b)};
+              s0 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s0)));
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -304,10 +318,9 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
                   k0[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
             }
             if (two) {
-              const int b1 = b + 1;
-              const double2 G0 = FLD2(q, 3 * b1), G1 = FLD2(q, 3 * b1 + 1), G2 = FLD2(q, 3 * b1 + 2);
-              const double gb[3] = {G0.x, G0.y, G1.x};
-              s1 = fma(ga[q][0], G1.y, fma(ga[q][1], G2.x, fma(ga[q][2], G2.y, s1)));
+              const double2 G = GA2(q, b + 1);
+              const double gb[3] = {G.x, G.y, G2D(q, b + 1)};
+              s1 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s1)));
 #pragma unroll
               for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -337,7 +350,8 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
 #pragma unroll
             for (int it = 0; it < 9; ++it) {
               const double2 v = tile[it * 32 + lane];
-              if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + goff[it]) = v;
+              const int off = goff[it * 32 + lane];
+              if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + off) = v;
             }
             __syncwarp();
           } else {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
@@ -359,7 +373,11 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         }
       }
   }
-#undef FLD2
+#undef GA2
+#undef TA2
+#undef LM2
+#undef G2D
+#undef T2D
 }
 
 }  // namespace fea

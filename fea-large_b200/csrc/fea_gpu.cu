@@ -79,6 +79,7 @@ struct fea_gpu_ctx {
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
   int gather_threads = 256;
+  int gather_split = 4;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;
@@ -238,6 +239,9 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   c->ne_pad = (pl.n_elems + 31) / 32 * 32;
   c->nnzb = pl.nnzb();
   c->n_slots = pl.n_slots();
+  // tuning knobs for A/B runs of the whole test suite (fea_gpu_set_param does the same per context)
+  if (const char *s = getenv("FEA_GATHER_THREADS")) fea_gpu_set_param(c, "gather_threads", atof(s));
+  if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
     int v = atoi(s);
     if (v >= 1 && v <= 4096) c->pcg_batch = v;
@@ -577,7 +581,7 @@ extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
 template <int MODEL, int NG>
 static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
   const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
-  const size_t smem = sizeof(double2) * NG * (fea::NF2 * 32 + fea::TILE_D2);
+  const size_t smem = sizeof(double) * NG * fea::FLD_DOUBLES + sizeof(double2) * NG * fea::TILE_D2 + sizeof(int) * 9 * 32;
 #define FEA_LAUNCH(K, Rr)                                                                          \
   do {                                                                                             \
     auto kern = fea::element_kernel<MODEL, NG, K, Rr>;                                             \
@@ -630,9 +634,17 @@ static fea::SellMat sell_mat(fea_gpu_ctx *c) {
 
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
-  const int grid = c->plan.n_slices;   // one CTA per slice, dispatched in slice order (L2 locality)
-  fea::gather_blocks_kernel<<<grid, c->gather_threads, 0, c->stream>>>(sell_mat(c), c->cptr, c->csrc, c->Ke,
-                                                         with_bc ? c->pflag : nullptr);
+  const uint8_t *pf = with_bc ? c->pflag : nullptr;
+  {
+    const int sp = c->gather_split;
+    const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
+    switch (c->gather_threads) {
+      case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
+      case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
+      case 128: fea::gather_blocks_kernel<128, 8><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
+      default: fea::gather_blocks_kernel<256, 5><<<grid, 256, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
+    }
+  }
   LAUNCHED();
   phase_end(c, PH_GATHER_K);
   return FEA_GPU_OK;
@@ -661,11 +673,20 @@ extern "C" int fea_gpu_assemble_residual(fea_gpu_handle c) {
   TRY(element_pass(c, false, true));
   return gather_residual(c);
 }
-extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t with_stiffness) {
+extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t flags) {
   CHECK_H(c);
-  TRY(element_pass(c, with_stiffness != 0, true));
-  if (with_stiffness) TRY(gather_stiffness(c, false));
-  return gather_residual(c);
+  const bool with_k = (flags & FEA_ASSEMBLE_STIFFNESS) != 0, fuse_bc = (flags & FEA_ASSEMBLE_FUSE_BC) != 0;
+  TRY(element_pass(c, with_k, true));
+  if (with_k) TRY(gather_stiffness(c, fuse_bc));
+  if (!fuse_bc) return gather_residual(c);
+  // solver_apply_prescribed_bc(self, 0) folded into the two gathers: rows and columns of prescribed
+  // DOFs cancelled keeping the diagonal, their right-hand side rows zero (fea_solver.c:1244-1257)
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, c->pflag);
+  LAUNCHED();
+  phase_end(c, PH_GATHER_R);
+  return FEA_GPU_OK;
 }
 
 extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
@@ -1045,7 +1066,8 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   if (!c || !name) return FEA_GPU_ERR_ARG;
   const std::string k(name);
   const int v = (int)value;
-  if (k == "gather_threads" && (v == 64 || v == 128 || v == 256)) c->gather_threads = v;
+  if (k == "gather_threads" && (v == 128 || v == 256 || v == 512 || v == 1024)) c->gather_threads = v;
+  else if (k == "gather_split" && v >= 1 && v <= 8) c->gather_split = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else {

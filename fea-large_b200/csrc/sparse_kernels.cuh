@@ -91,62 +91,88 @@ struct SellMat {
 // of the precomputed list (ascending global element id = the reference's element-major
 // accumulation, fea_solver.c:878-882), so results are bit-reproducible run to run and need
 // no atomics.  Optionally applies the Dirichlet cancellation in the same pass.
-// Launch: one CTA per slice (grid = n_slices), its warps take the slot columns round-robin.
-// CTAs are dispatched in slice order, so the slices in flight at any time (a few per SM) come
-// from a handful of neighbouring sigma-windows: the K_e staging they read (~40 MB) stays in L2
-// and the second reader of every symmetric block hits there instead of DRAM (v2 with one warp
-// per slice and 9.5 k slices in flight read 17.4 GB from DRAM for 7.2 GB of blocks).
-__global__ void __launch_bounds__(256)
-gather_blocks_kernel(SellMat A, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
-                     const double *__restrict__ Ke, const uint8_t *__restrict__ pflag /* may be null */) {
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int s = blockIdx.x; s < A.n_slices; s += gridDim.x) {
-    const int base = A.slice_ptr[s];
-    const int width = (A.slice_ptr[s + 1] - base) >> 5;
+// Work item = one slot column of one slice (32 slots, one warp).
+__device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__restrict__ cptr,
+                                            const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
+                                            const uint8_t *__restrict__ pflag, int s, int j, int lane) {
+  const int base = A.slice_ptr[s];
+  const int slot = base + (j << 5) + lane;
+  const int k0 = cptr[slot], k1 = cptr[slot + 1];
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = k0; k < k1; ++k) {
+    const uint32_t src = csrc[k];
+    const uint32_t idx = src & 0x7fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
+    const size_t off = (size_t)idx * 9 + idx / 11u;
+    // 72 bytes at an 8-byte boundary: five 16-byte loads of the enclosing aligned 80 bytes (the
+    // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones --
+    // every load of a lane lands in a different cache line, so L1 tag lookups drop by 9/5
+    const double2 *p = reinterpret_cast<const double2 *>(Ke + (off & ~(size_t)1));
+    const bool odd = (off & 1) != 0;
+    double w[10];
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const double2 t = p[h];
+      w[2 * h] = t.x;
+      w[2 * h + 1] = t.y;
+    }
+    double v[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = odd ? w[c + 1] : w[c];
+    if (src >> 31) {  // stored block is K_e[b][a]: add its transpose
+#pragma unroll
+      for (int c = 0; c < 9; ++c) acc[c] += v[(c % 3) * 3 + c / 3];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) acc[c] += v[c];
+    }
+  }
+  if (pflag) {
     const int row = A.sell_row[s * 32 + lane];
     uint8_t rf0 = 0, rf1 = 0, rf2 = 0;
-    if (pflag && row >= 0) {
+    if (row >= 0) {
       rf0 = pflag[3 * (size_t)row];
       rf1 = pflag[3 * (size_t)row + 1];
       rf2 = pflag[3 * (size_t)row + 2];
     }
-    for (int j = warp; j < width; j += nwarps) {
-      const int slot = base + (j << 5) + lane;
-      const int k0 = cptr[slot], k1 = cptr[slot + 1];
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int k = k0; k < k1; ++k) {
-        const uint32_t src = csrc[k];
-        const uint32_t idx = src & 0x7fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
-        const double *b = Ke + ((size_t)idx * 9 + idx / 11u);
-        double v[9];
+    const int col = A.bcol[slot];
+    const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
+    const bool dg = (col == row);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) v[c] = b[c];
-        if (src >> 31) {  // stored block is K_e[b][a]: add its transpose
-#pragma unroll
-          for (int c = 0; c < 9; ++c) acc[c] += v[(c % 3) * 3 + c / 3];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 9; ++c) acc[c] += v[c];
-        }
-      }
-      if (pflag) {
-        const int col = A.bcol[slot];
-        const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
-        const bool dg = (col == row);
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-          const int i = c / 3, jj = c % 3;
-          const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
-          const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
-          if ((rf | cf) && !(dg && i == jj)) acc[c] = 0.0;
-        }
-      }
-      double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
-#pragma unroll
-      for (int c = 0; c < 9; ++c) out[c * 32] = acc[c];
+    for (int c = 0; c < 9; ++c) {
+      const int i = c / 3, jj = c % 3;
+      const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
+      const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
+      if ((rf | cf) && !(dg && i == jj)) acc[c] = 0.0;
     }
   }
+  double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) out[c * 32] = acc[c];
+}
+
+// `split` consecutive CTAs per slice, their warps take the slot columns round-robin.  CTAs are
+// dispatched in slice order, so the slices in flight are (resident CTAs) / split, and that window
+// is what decides the DRAM traffic: every staged block has two readers (slot (i,j) and, transposed,
+// slot (j,i)), and the second one only hits L2 if the window's staging (~166 KB per slice) fits
+// there.  Measured on C3 (profiles/r1b_gather_variants.md): one warp per slice (9.5 k slices in
+// flight) read 17.4 GB from DRAM for 7.2 GB of blocks; one 256-thread CTA per slice (740 in flight)
+// 9.2 GB; 512 threads 6.9 GB; 1024 threads 4.9 GB -- but fat CTAs lose to drain/launch gaps, while
+// 4 CTAs of 256 threads per slice keep 40 warps per SM on 185 slices: 2.34 -> 2.03 ms.
+// Dealing single columns to a persistent grid (no slice affinity: L1 reuse between the columns of a
+// row is lost and the warps drift apart, 16 GB) and a warp-per-row mapping with lanes over (column,
+// component) (coalesced 72-byte reads, but one 8-byte load in flight per lane) were both slower.
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
+                           const double *__restrict__ Ke, const uint8_t *__restrict__ pflag /* may be null */) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
+  // `split` consecutive CTAs share a slice (columns dealt round-robin over their warps): the same
+  // number of resident warps then covers `split` times fewer slices, i.e. a smaller L2 footprint
+  const int s = blockIdx.x / split, part = blockIdx.x - s * split;
+  if (s >= A.n_slices) return;
+  const int width = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
+  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, pflag, s, j, lane);
 }
 
 // residual gather: R[3I+i] = sum over (element, a) touching node I of R_e[a][i]

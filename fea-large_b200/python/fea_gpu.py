@@ -239,9 +239,9 @@ class FeaGpu:
         _check(lib().fea_gpu_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
-    def assemble_all(self, with_stiffness=True):
+    def assemble_all(self, with_stiffness=True, fuse_bc=False):
         lib().fea_gpu_assemble_all.argtypes = [C.c_void_p, C.c_int32]
-        _check(lib().fea_gpu_assemble_all(self.h, int(with_stiffness)))
+        _check(lib().fea_gpu_assemble_all(self.h, (1 if with_stiffness else 0) | (2 if fuse_bc else 0)))
 
     def apply_increment(self, lam=1.0):
         lib().fea_gpu_apply_increment.argtypes = [C.c_void_p, C.c_double]

@@ -98,8 +98,13 @@ int fea_gpu_update_state(fea_gpu_handle h);
 int fea_gpu_assemble_stiffness(fea_gpu_handle h);
 /* solver_create_residual_forces (:863, :1072-1114): global_forces_vct = -int sigma grad N */
 int fea_gpu_assemble_residual(fea_gpu_handle h);
-/* state + stiffness + residual from the current nodes in ONE element pass */
-int fea_gpu_assemble_all(fea_gpu_handle h, int32_t with_stiffness);
+/* state + stiffness + residual from the current nodes in ONE element pass.
+ * flags: FEA_ASSEMBLE_STIFFNESS also rebuilds K (0 = modified-Newton iteration, R only);
+ * FEA_ASSEMBLE_FUSE_BC folds solver_apply_prescribed_bc(self, 0) (:1200, :1244-1257) into the two
+ * gathers -- bitwise what fea_gpu_apply_bc(h, 0) gives afterwards, one sweep over K less */
+#define FEA_ASSEMBLE_STIFFNESS 1
+#define FEA_ASSEMBLE_FUSE_BC 2
+int fea_gpu_assemble_all(fea_gpu_handle h, int32_t flags);
 /* solver_apply_prescribed_bc(self, lambda) (:1200, :1244-1257 + sp_matrix_cross_cancellation) */
 int fea_gpu_apply_bc(fea_gpu_handle h, double lambda);
 /* keep / restore the assembled matrix: sp_matrix_copy at :179 and :194-195 (modified Newton) */

@@ -91,6 +91,17 @@ def test_fused_pass_equals_phase_calls(brick):
     assert all(np.array_equal(p, q) for p, q in zip(a.get_state(), b.get_state()))
 
 
+def test_fused_bc_equals_apply_bc(brick):
+    """FEA_ASSEMBLE_FUSE_BC must give bitwise what assemble_all + apply_bc(0) give."""
+    name, m, _ = brick
+    a, b = make_gpu(m), make_gpu(m)
+    x = deformed(m, 6)
+    a.set_nodes(x); a.assemble_all(True); a.apply_bc(0.0)
+    b.set_nodes(x); b.assemble_all(True, fuse_bc=True)
+    assert np.array_equal(a.get_csr()[3], b.get_csr()[3])
+    assert np.array_equal(a.get_forces(), b.get_forces())
+
+
 def test_host_buffer_step_equals_phase_calls(brick):
     """fea_gpu_step_from_host (host nodes in, host residual out, BC fused into the gather) must give
     exactly what assemble_all + apply_bc(0) give -- with pinned and with ordinary host arrays."""
