@@ -51,6 +51,7 @@ struct ElemArgs {
   const double *X0;            // [n_local][3]
   const double *x;             // [n_local][3]
   double lambda, mu;
+  double rho;                  // lambda / mu (RATIO kernels only)
   double *F_soa;               // [ng*9][ne_pad]   (may be null)
   double *S_soa;               // [ng*9][ne_pad]
   double *Ke;                  // [n_elems][KE_STRIDE]  a<=b node-pair blocks, layout in fea_plan.hpp
@@ -78,7 +79,7 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
   o[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
 }
 
-template <int MODEL, int NG, bool WITH_K, bool WITH_R>
+template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO>
 __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
@@ -94,13 +95,31 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   // the NG warps of the CTA fetch the 10 nodes of the 32 elements once (coalesced connectivity,
   // gathered coordinates) into the region the store tiles will use later: [node][x0..2,X0..2][lane]
   double *coords = reinterpret_cast<double *>(tiles);
-  for (int a = gp; a < 10; a += NG) {
-    const int node = live ? A.conn_soa[(size_t)a * A.ne_pad + e] : 0;
-    const double *xk = A.x + 3 * (size_t)node, *Xk = A.X0 + 3 * (size_t)node;
+  {
+    constexpr int NA = (10 + NG - 1) / NG;   // nodes per warp: both index loads, then all coordinate
+    int node[NA];                            // loads, are in flight together (one round trip each)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      coords[((a * 6 + d) * 32) + lane] = xk[d];
-      coords[((a * 6 + 3 + d) * 32) + lane] = Xk[d];
+    for (int i = 0; i < NA; ++i) {
+      const int a = gp + i * NG;
+      node[i] = (live && a < 10) ? A.conn_soa[(size_t)a * A.ne_pad + e] : 0;
+    }
+    double cx[NA][6];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const double *xk = A.x + 3 * (size_t)node[i], *Xk = A.X0 + 3 * (size_t)node[i];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        cx[i][d] = xk[d];
+        cx[i][3 + d] = Xk[d];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int a = gp + i * NG;
+      if (a < 10) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) coords[((a * 6 + d) * 32) + lane] = cx[i][d];
+      }
     }
   }
   if (WITH_K && gp == 0) {
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   // blocks, two consecutive ones at a time.  With t symmetric in sigma, g_a . t_b = t_a . g_b, so
   //   K_ab[i][j] = sum_q  u_ai g_bj + v_aj g_bi + d_ij t_a . g_b,   u = lam' wd g_a, v = mu' wd g_a
   // and the column side streams 24 bytes per Gauss point from shared memory; u, v, t of the row stay
-  // in registers.  The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of
+  // in registers (RATIO kernels: A5 with mu != 0, where u = (lambda / mu) v, keep only v and t).  The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of
   // the same loads.
 #define GA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + (b)*64)[lane]
 #define TA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_TA + (b)*64)[lane]
@@ -267,7 +286,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     for (int pr = gp; pr < 5; pr += NG)
       for (int half = 0; half < 2; ++half) {
         const int a = half ? 9 - pr : pr;
-        double ua[NG][3], va[NG][3], ta[NG][3];
+        double ua[RATIO ? 1 : NG][3], va[NG][3], ta[NG][3];
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
@@ -276,9 +295,11 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           ta[q][0] = T.x;
           ta[q][1] = T.y;
           ta[q][2] = T2D(q, a);
-          ua[q][0] = LM.x * G.x;
-          ua[q][1] = LM.x * G.y;
-          ua[q][2] = LM.x * g2;
+          if (!RATIO) {
+            ua[q][0] = LM.x * G.x;
+            ua[q][1] = LM.x * G.y;
+            ua[q][2] = LM.x * g2;
+          }
           // explicitly rounded: the residual must not depend on whether K is built in the same pass
           va[q][0] = __dmul_rn(LM.y, G.x);
           va[q][1] = __dmul_rn(LM.y, G.y);
@@ -315,7 +336,8 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
               for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                  k0[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
+                  k0[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k0[3 * i + j])
+                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
             }
             if (two) {
               const double2 G = GA2(q, b + 1);
@@ -325,8 +347,34 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
               for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                  k1[3 * i + j] = fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
+                  k1[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k1[3 * i + j])
+                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
             }
+          }
+          if (RATIO) {
+            // A5: lam' / mu' = lambda / mu at every Gauss point, so u_a = rho v_a and with
+            // P = sum_q v_a (x) g_b the block is rho P + P^T (+ the diagonal term): 12 instead of 21
+            // FMAs per Gauss point and no u in registers
+            const double rho = A.rho;
+            const double p01 = k0[1], p02 = k0[2], p12 = k0[5], q01 = k1[1], q02 = k1[2], q12 = k1[5];
+            k0[0] = fma(rho, k0[0], k0[0]);
+            k0[4] = fma(rho, k0[4], k0[4]);
+            k0[8] = fma(rho, k0[8], k0[8]);
+            k0[1] = fma(rho, p01, k0[3]);
+            k0[3] = fma(rho, k0[3], p01);
+            k0[2] = fma(rho, p02, k0[6]);
+            k0[6] = fma(rho, k0[6], p02);
+            k0[5] = fma(rho, p12, k0[7]);
+            k0[7] = fma(rho, k0[7], p12);
+            k1[0] = fma(rho, k1[0], k1[0]);
+            k1[4] = fma(rho, k1[4], k1[4]);
+            k1[8] = fma(rho, k1[8], k1[8]);
+            k1[1] = fma(rho, q01, k1[3]);
+            k1[3] = fma(rho, k1[3], q01);
+            k1[2] = fma(rho, q02, k1[6]);
+            k1[6] = fma(rho, k1[6], q02);
+            k1[5] = fma(rho, q12, k1[7]);
+            k1[7] = fma(rho, k1[7], q12);
           }
           k0[0] += s0;
           k0[4] += s0;

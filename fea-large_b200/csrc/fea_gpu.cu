@@ -79,6 +79,7 @@ struct fea_gpu_ctx {
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
   int gather_threads = 256;
+  bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 4;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
 
   double *X0 = nullptr, *x = nullptr;
@@ -90,6 +91,7 @@ struct fea_gpu_ctx {
   double *vals = nullptr, *vals_saved = nullptr;
   double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr, *u_saved = nullptr;
   uint8_t *pflag = nullptr;
+  uint8_t *sflag = nullptr;        // [n_slots] bits 0-2 row DOFs prescribed, 3-5 column DOFs, 6 diagonal block
   double *pval = nullptr;
   int32_t *inc_dof = nullptr;
   double *inc_val = nullptr;
@@ -319,6 +321,25 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
         ival.push_back(inc[t]);
       }
     c->n_inc = (int)idof.size();
+    {
+      std::vector<uint8_t> sf((size_t)pl.n_slots(), 0);
+      for (int32_t sl = 0; sl < pl.n_slices; ++sl) {
+        const int32_t base = pl.slice_ptr[(size_t)sl], width = (pl.slice_ptr[(size_t)sl + 1] - base) / fea::SELL_C;
+        for (int l = 0; l < fea::SELL_C; ++l) {
+          const int32_t row = pl.sell_row[(size_t)sl * fea::SELL_C + l];
+          if (row < 0) continue;
+          const unsigned rf = flag[3 * (size_t)row] | (flag[3 * (size_t)row + 1] << 1) | (flag[3 * (size_t)row + 2] << 2);
+          for (int32_t j = 0; j < width; ++j) {
+            const size_t slot = (size_t)base + (size_t)j * fea::SELL_C + l;
+            const int32_t col = pl.sbcol[slot];
+            const unsigned cf = flag[3 * (size_t)col] | (flag[3 * (size_t)col + 1] << 1) | (flag[3 * (size_t)col + 2] << 2);
+            sf[slot] = (uint8_t)(rf | (cf << 3) | (col == row ? 64u : 0u));
+          }
+        }
+      }
+      TRY(dev_upload(&c->sflag, sf, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
     TRY(dev_upload(&c->pflag, flag, c->stream));
     TRY(dev_upload(&c->pval, val, c->stream));
     TRY(dev_upload(&c->inc_dof, idof, c->stream));
@@ -447,7 +468,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (c->has_comm) ncclCommDestroy(c->comm);
   void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->slice_ptr, c->sell_row, c->bcol,
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
-                  c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->pval, c->inc_dof, c->inc_val,
+                  c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
                   c->flush, c->export_buf};
   for (void *p : ptrs)
@@ -578,13 +599,13 @@ extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
 // ---------------------------------------------------------------------------------
 // element pass
 
-template <int MODEL, int NG>
+template <int MODEL, int NG, bool RATIO>
 static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
   const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
   const size_t smem = sizeof(double) * NG * fea::FLD_DOUBLES + sizeof(double2) * NG * fea::TILE_D2 + sizeof(int) * 9 * 32;
 #define FEA_LAUNCH(K, Rr)                                                                          \
   do {                                                                                             \
-    auto kern = fea::element_kernel<MODEL, NG, K, Rr>;                                             \
+    auto kern = fea::element_kernel<MODEL, NG, K, Rr, RATIO>;                                      \
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kern<<<grid, NG * 32, smem, c->stream>>>(args);                                                \
   } while (0)
@@ -614,10 +635,15 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
   CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
   phase_begin(c, PH_ELEM);
   int rc;
-  if (c->model == FEA_MODEL_A5)
-    rc = c->ng == 5 ? launch_element<0, 5>(c, with_k, with_r, a) : launch_element<0, 4>(c, with_k, with_r, a);
+  // A5 with mu != 0: lam' / mu' is the same at every Gauss point (element_kernels.cuh, RATIO)
+  a.rho = c->mu != 0.0 ? c->lambda / c->mu : 0.0;
+  const bool ratio = c->model == FEA_MODEL_A5 && c->mu != 0.0 && std::isfinite(a.rho) && c->elem_ratio;
+  if (c->model == FEA_MODEL_A5 && ratio)
+    rc = c->ng == 5 ? launch_element<0, 5, true>(c, with_k, with_r, a) : launch_element<0, 4, true>(c, with_k, with_r, a);
+  else if (c->model == FEA_MODEL_A5)
+    rc = c->ng == 5 ? launch_element<0, 5, false>(c, with_k, with_r, a) : launch_element<0, 4, false>(c, with_k, with_r, a);
   else
-    rc = c->ng == 5 ? launch_element<1, 5>(c, with_k, with_r, a) : launch_element<1, 4>(c, with_k, with_r, a);
+    rc = c->ng == 5 ? launch_element<1, 5, false>(c, with_k, with_r, a) : launch_element<1, 4, false>(c, with_k, with_r, a);
   phase_end(c, PH_ELEM);
   return rc;
 }
@@ -634,7 +660,7 @@ static fea::SellMat sell_mat(fea_gpu_ctx *c) {
 
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
-  const uint8_t *pf = with_bc ? c->pflag : nullptr;
+  const uint8_t *pf = with_bc ? c->sflag : nullptr;
   {
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
@@ -728,7 +754,7 @@ extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
     LAUNCHED();
   }
   const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), 148 * 32);
-  fea::cancel_kernel<<<grid, 256, 0, c->stream>>>(sell_mat(c), c->pflag);
+  fea::cancel_kernel<<<grid, 256, 0, c->stream>>>(sell_mat(c), c->sflag);
   LAUNCHED();
   fea::rhs_fix_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->pflag, c->pval, lambda, c->R);
   LAUNCHED();
@@ -1067,6 +1093,7 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   const std::string k(name);
   const int v = (int)value;
   if (k == "gather_threads" && (v == 128 || v == 256 || v == 512 || v == 1024)) c->gather_threads = v;
+  else if (k == "elem_ratio" && (v == 0 || v == 1)) c->elem_ratio = v != 0;
   else if (k == "gather_split" && v >= 1 && v <= 8) c->gather_split = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;

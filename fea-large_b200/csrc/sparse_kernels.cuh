@@ -90,11 +90,12 @@ struct SellMat {
 // K3: gather assembly.  Each lane owns one block slot and sums its contributions in the order
 // of the precomputed list (ascending global element id = the reference's element-major
 // accumulation, fea_solver.c:878-882), so results are bit-reproducible run to run and need
-// no atomics.  Optionally applies the Dirichlet cancellation in the same pass.
+// no atomics.  Optionally applies the Dirichlet cancellation in the same pass, from one flag byte
+// per slot (the prescribed DOFs are fixed when the context is created).
 // Work item = one slot column of one slice (32 slots, one warp).
 __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__restrict__ cptr,
                                             const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
-                                            const uint8_t *__restrict__ pflag, int s, int j, int lane) {
+                                            const uint8_t *__restrict__ sflag, int s, int j, int lane) {
   const int base = A.slice_ptr[s];
   const int slot = base + (j << 5) + lane;
   const int k0 = cptr[slot], k1 = cptr[slot + 1];
@@ -126,23 +127,14 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
       for (int c = 0; c < 9; ++c) acc[c] += v[c];
     }
   }
-  if (pflag) {
-    const int row = A.sell_row[s * 32 + lane];
-    uint8_t rf0 = 0, rf1 = 0, rf2 = 0;
-    if (row >= 0) {
-      rf0 = pflag[3 * (size_t)row];
-      rf1 = pflag[3 * (size_t)row + 1];
-      rf2 = pflag[3 * (size_t)row + 2];
-    }
-    const int col = A.bcol[slot];
-    const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
-    const bool dg = (col == row);
+  if (sflag) {
+    const unsigned f = sflag[slot];   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
+    if (f & 63u) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      const int i = c / 3, jj = c % 3;
-      const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
-      const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
-      if ((rf | cf) && !(dg && i == jj)) acc[c] = 0.0;
+      for (int c = 0; c < 9; ++c) {
+        const int i = c / 3, jj = c % 3;
+        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) acc[c] = 0.0;
+      }
     }
   }
   double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
@@ -164,7 +156,7 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
-                           const double *__restrict__ Ke, const uint8_t *__restrict__ pflag /* may be null */) {
+                           const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
   // `split` consecutive CTAs share a slice (columns dealt round-robin over their warps): the same
@@ -172,7 +164,7 @@ gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, con
   const int s = blockIdx.x / split, part = blockIdx.x - s * split;
   if (s >= A.n_slices) return;
   const int width = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
-  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, pflag, s, j, lane);
+  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, sflag, s, j, lane);
 }
 
 // residual gather: R[3I+i] = sum over (element, a) touching node I of R_e[a][i]
@@ -196,28 +188,20 @@ gather_residual_kernel(int n_rows, const int32_t *__restrict__ rptr, const int32
 // K4: zero rows and columns of prescribed DOFs keeping the diagonal (sp_matrix_cross_cancellation
 // as used at fea_solver.c:1255); RHS rows become diag * presc (:1256)
 __global__ void __launch_bounds__(256)
-cancel_kernel(SellMat A, const uint8_t *__restrict__ pflag) {
+cancel_kernel(SellMat A, const uint8_t *__restrict__ sflag) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < A.n_slices; s += warps_per_grid) {
     const int base = A.slice_ptr[s];
     const int width = (A.slice_ptr[s + 1] - base) >> 5;
-    const int row = A.sell_row[s * 32 + lane];
-    if (row < 0) continue;
-    const uint8_t rf0 = pflag[3 * (size_t)row], rf1 = pflag[3 * (size_t)row + 1], rf2 = pflag[3 * (size_t)row + 2];
     for (int j = 0; j < width; ++j) {
-      const int slot = base + (j << 5) + lane;
-      const int col = A.bcol[slot];
-      const uint8_t cf0 = pflag[3 * (size_t)col], cf1 = pflag[3 * (size_t)col + 1], cf2 = pflag[3 * (size_t)col + 2];
-      if (!(rf0 | rf1 | rf2 | cf0 | cf1 | cf2)) continue;
-      const bool dg = (col == row);
+      const unsigned f = sflag[base + (j << 5) + lane];   // per-slot flags, see gather_item
+      if (!(f & 63u)) continue;
       double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         const int i = c / 3, jj = c % 3;
-        const uint8_t rf = i == 0 ? rf0 : (i == 1 ? rf1 : rf2);
-        const uint8_t cf = jj == 0 ? cf0 : (jj == 1 ? cf1 : cf2);
-        if ((rf | cf) && !(dg && i == jj)) out[c * 32] = 0.0;
+        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) out[c * 32] = 0.0;
       }
     }
   }

@@ -102,6 +102,24 @@ def test_fused_bc_equals_apply_bc(brick):
     assert np.array_equal(a.get_forces(), b.get_forces())
 
 
+def test_a5_ratio_form_matches_generic_form():
+    """A5 blocks built as rho P + P^T (lam'/mu' = lambda/mu at every Gauss point) against the generic
+    two-coefficient form of the same kernel, and mu = 0 (no ratio) against the oracle."""
+    m, _ = load_golden("a5_brick")
+    a, b = make_gpu(m), make_gpu(m)
+    b.set_param("elem_ratio", 0)
+    x = deformed(m, 9)
+    for s in (a, b):
+        s.set_nodes(x); s.assemble_all(True)
+    assert relmax(a.get_csr()[3], b.get_csr()[3]) < 1e-13
+    assert np.array_equal(a.get_forces(), b.get_forces())
+    m.mu = 0.0
+    g, o = make_gpu(m), PortOracle(m)
+    for s in (g, o):
+        s.set_nodes(x); s.update_state(); s.assemble_stiffness()
+    assert relmax(g.get_csr()[3], o.get_csr()[2]) < RTOL_ELEM
+
+
 def test_host_buffer_step_equals_phase_calls(brick):
     """fea_gpu_step_from_host (host nodes in, host residual out, BC fused into the gather) must give
     exactly what assemble_all + apply_bc(0) give -- with pinned and with ordinary host arrays."""
