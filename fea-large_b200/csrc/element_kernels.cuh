@@ -15,7 +15,8 @@
 // registers; its results cross to phase B through shared memory laid out
 // [gauss][field][lane] in 16-byte fields (conflict-free LDS.128/STS.128).  Phase B gives warp
 // w the eleven a<=b blocks of staging region w (rows w and 9-w, fea_plan.hpp) of its lane's
-// element, two consecutive blocks at a time, summed over the Gauss points.
+// element, one block at a time, summed over the Gauss points.  38 doubles per (element, Gauss
+// point) cross over -- 73 KB of shared memory per CTA, three CTAs (15 warps) per SM.
 //
 // Closed form used for the tangent (both models):
 //   c^_ikjl = lam' d_ik d_jl + mu' (d_ij d_kl + d_il d_jk)
@@ -31,11 +32,13 @@ namespace fea {
 
 constexpr int ELEMS_PER_CTA = 32;
 // Hand-over fields per Gauss point, [field][lane] (lane-contiguous: conflict-free):
-//   double2 GA[b] = (g0,g1) and TA[b] = (t0,t1) for the 10 nodes, double2 LM = (lam' wd, mu' wd),
-//   then plain doubles g2[b], t2[b].  g = grad N_b, t = (mu' wd I + wd sigma) g.
-// The column side of a block needs only g (24 bytes per Gauss point), the row side g and t.
-constexpr int FLD_DOUBLES = 62 * 32;          // doubles per Gauss point
-constexpr int FLD_TA = 10 * 64, FLD_LM = 20 * 64, FLD_G2 = 21 * 64, FLD_T2 = 21 * 64 + 10 * 32;
+//   double2 GA[b] = (g0,g1) for the 10 nodes, three double2 of the symmetric
+//   s' = mu' wd I + wd sigma: (s00,s01), (s02,s11), (s12,s22), double2 LM = (lam' wd, mu' wd),
+//   then plain doubles g2[b].  g = grad N_b in the current configuration, wd = w |det J|.
+// The column side of a block needs only g (24 bytes per Gauss point); the row side forms
+// t_a = s' g_a itself (9 FMAs per Gauss point and row) instead of reading it.
+constexpr int FLD_DOUBLES = 38 * 32;          // doubles per Gauss point
+constexpr int FLD_SG = 10 * 64, FLD_LM = 13 * 64, FLD_G2 = 14 * 64;
 constexpr int TILE_D2 = 9 * 32;               // double2 per warp: the store-transpose tile of one block pair
 
 struct ElemTables {
@@ -79,8 +82,8 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
   o[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
 }
 
-template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO>
-__global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
+template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO, int OCC>
+__global__ void __launch_bounds__(NG * 32, OCC) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
   double2 *tiles = reinterpret_cast<double2 *>(fld + NG * FLD_DOUBLES);  // [NG][TILE_D2] store tiles
@@ -154,27 +157,26 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     double Ji[3][3];
     inv3(J, ok ? detJ : 1.0, Ji);
 
-    // g[i][a] = sum_k J^-1[i][k] dN[k][a]       (:714-718)
-    double g[3][10];
+    // g[i][a] = sum_k J^-1[i][k] dN[k][a]       (:714-718), handed over node by node, and
+    // F^-1[i][j] = sum_k g[j][k] X0_k,i, then inverted  (:1141-1152)
+    double *my = fld + gp * FLD_DOUBLES;
+    double Fi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
     for (int a = 0; a < 10; ++a) {
       const double d0 = c_tab.dN[gp][0][a], d1 = c_tab.dN[gp][1][a], d2 = c_tab.dN[gp][2][a];
+      double ga[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) g[i][a] = Ji[i][0] * d0 + Ji[i][1] * d1 + Ji[i][2] * d2;
-    }
-
-    // F^-1[i][j] = sum_k g[j][k] X0_k,i, then invert  (:1141-1152)
-    double Fi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const double X0 = coords[(k * 6 + 3) * 32 + lane], X1 = coords[(k * 6 + 4) * 32 + lane],
-                   X2 = coords[(k * 6 + 5) * 32 + lane];
+      for (int i = 0; i < 3; ++i) ga[i] = Ji[i][0] * d0 + Ji[i][1] * d1 + Ji[i][2] * d2;
+      const double X0 = coords[(a * 6 + 3) * 32 + lane], X1 = coords[(a * 6 + 4) * 32 + lane],
+                   X2 = coords[(a * 6 + 5) * 32 + lane];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        Fi[0][j] = fma(g[j][k], X0, Fi[0][j]);
-        Fi[1][j] = fma(g[j][k], X1, Fi[1][j]);
-        Fi[2][j] = fma(g[j][k], X2, Fi[2][j]);
+        Fi[0][j] = fma(ga[j], X0, Fi[0][j]);
+        Fi[1][j] = fma(ga[j], X1, Fi[1][j]);
+        Fi[2][j] = fma(ga[j], X2, Fi[2][j]);
       }
+      reinterpret_cast<double2 *>(my + a * 64)[lane] = make_double2(ok ? ga[0] : 0.0, ok ? ga[1] : 0.0);
+      my[FLD_G2 + a * 32 + lane] = ok ? ga[2] : 0.0;
     }
     const double detFi = det3(Fi);
     double F[3][3];
@@ -240,40 +242,27 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         atomicAdd(A.bad, 1ULL);
     }
 
-    // hand over to phase B: g, t = (mu' I + sigma) g scaled by wd, and the scaled coefficients
+    // hand over to phase B: s' = mu' wd I + wd sigma and the scaled coefficients
     const double wd = ok ? c_tab.w[gp] * fabs(detJ) : 0.0;  // fabs: fea_solver.c:958,1047,1104
     const double lw = lam1 * wd, mw = mu1 * wd;
-    double *my = fld + gp * FLD_DOUBLES;
-#pragma unroll
-    for (int a = 0; a < 10; ++a) {
-      double gg[3], tt[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double sg = S[i][0] * g[0][a] + S[i][1] * g[1][a] + S[i][2] * g[2][a];
-        gg[i] = ok ? g[i][a] : 0.0;
-        tt[i] = ok ? fma(wd, sg, mw * g[i][a]) : 0.0;
-      }
-      reinterpret_cast<double2 *>(my + a * 64)[lane] = make_double2(gg[0], gg[1]);
-      reinterpret_cast<double2 *>(my + FLD_TA + a * 64)[lane] = make_double2(tt[0], tt[1]);
-      my[FLD_G2 + a * 32 + lane] = gg[2];
-      my[FLD_T2 + a * 32 + lane] = tt[2];
-    }
+    reinterpret_cast<double2 *>(my + FLD_SG)[lane] = make_double2(ok ? fma(wd, S[0][0], mw) : 0.0, ok ? wd * S[0][1] : 0.0);
+    reinterpret_cast<double2 *>(my + FLD_SG + 64)[lane] = make_double2(ok ? wd * S[0][2] : 0.0, ok ? fma(wd, S[1][1], mw) : 0.0);
+    reinterpret_cast<double2 *>(my + FLD_SG + 128)[lane] = make_double2(ok ? wd * S[1][2] : 0.0, ok ? fma(wd, S[2][2], mw) : 0.0);
     reinterpret_cast<double2 *>(my + FLD_LM)[lane] = make_double2(lw, mw);
   }
   __syncthreads();
 
   // ------------------------------ phase B ------------------------------------
   // Warp w takes staging region w (fea_plan.hpp): rows w and 9-w of the a<=b block triangle, eleven
-  // blocks, two consecutive ones at a time.  With t symmetric in sigma, g_a . t_b = t_a . g_b, so
+  // blocks.  With s' symmetric, g_a . t_b = t_a . g_b, so
   //   K_ab[i][j] = sum_q  u_ai g_bj + v_aj g_bi + d_ij t_a . g_b,   u = lam' wd g_a, v = mu' wd g_a
   // and the column side streams 24 bytes per Gauss point from shared memory; u, v, t of the row stay
-  // in registers (RATIO kernels: A5 with mu != 0, where u = (lambda / mu) v, keep only v and t).  The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of
-  // the same loads.
+  // in registers (RATIO kernels: A5 with mu != 0, where u = (lambda / mu) v, keep only v and t).
+  // The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of the same loads.
 #define GA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + (b)*64)[lane]
-#define TA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_TA + (b)*64)[lane]
+#define SG2(q, h) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_SG + (h)*64)[lane]
 #define LM2(q) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_LM)[lane]
 #define G2D(q, b) fld[(q)*FLD_DOUBLES + FLD_G2 + (b)*32 + lane]
-#define T2D(q, b) fld[(q)*FLD_DOUBLES + FLD_T2 + (b)*32 + lane]
 
   if (WITH_K || WITH_R) {
     double2 *tile = tiles + gp * TILE_D2;
@@ -290,17 +279,18 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-          const double2 G = GA2(q, a), T = TA2(q, a), LM = LM2(q);
+          const double2 G = GA2(q, a), S0 = SG2(q, 0), S1 = SG2(q, 1), S2 = SG2(q, 2), LM = LM2(q);
           const double g2 = G2D(q, a);
-          ta[q][0] = T.x;
-          ta[q][1] = T.y;
-          ta[q][2] = T2D(q, a);
+          // explicitly rounded where the compiler could fuse differently from one instantiation to
+          // the next: t, v and the residual must not depend on whether K is built in the same pass
+          ta[q][0] = fma(S0.x, G.x, fma(S0.y, G.y, __dmul_rn(S1.x, g2)));
+          ta[q][1] = fma(S0.y, G.x, fma(S1.y, G.y, __dmul_rn(S2.x, g2)));
+          ta[q][2] = fma(S1.x, G.x, fma(S2.x, G.y, __dmul_rn(S2.y, g2)));
           if (!RATIO) {
             ua[q][0] = LM.x * G.x;
             ua[q][1] = LM.x * G.y;
             ua[q][2] = LM.x * g2;
           }
-          // explicitly rounded: the residual must not depend on whether K is built in the same pass
           va[q][0] = __dmul_rn(LM.y, G.x);
           va[q][1] = __dmul_rn(LM.y, G.y);
           va[q][2] = __dmul_rn(LM.y, g2);
@@ -316,100 +306,56 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           A.Re[(size_t)(3 * a + 2) * A.ne_pad + e] = -r2;
         }
         if (!WITH_K) continue;
-        // Each thread builds two consecutive blocks (a,b), (a,b+1) of its element -- 144 contiguous,
-        // 16-byte aligned bytes of the staging -- and the warp transposes them through its tile so
-        // that the global stores are 16-byte pieces walking those 144-byte chunks with consecutive
-        // lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per request; v3
-        // transposed but spent ~25 instructions of index arithmetic per 8-byte store,
+        // Blocks (a,b), (a,b+1) at an even staging position are 144 contiguous, 16-byte aligned
+        // bytes of K_e.  Each thread drops its block into its row of the warp's tile; once the pair
+        // is there the warp stores it as 16-byte pieces walking those 144-byte chunks with
+        // consecutive lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per
+        // request; v3 transposed but spent ~25 instructions of index arithmetic per 8-byte store,
         // profiles/r1_v3_ncu_full_summary.md -- here the per-lane offsets come from a table.)
-        for (int b = a; b < 10; b += 2) {
-          const bool two = b + 1 < 10;   // warp-uniform
-          double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-          double s0 = 0.0, s1 = 0.0;
+        for (int b = a; b < 10; ++b) {
+          double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          double sd = 0.0;
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
-            {
-              const double2 G = GA2(q, b);
-              const double gb[3] = {G.x, G.y, G2D(q, b)};
-              s0 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s0)));
+            const double2 G = GA2(q, b);
+            const double gb[3] = {G.x, G.y, G2D(q, b)};
+            sd = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], sd)));
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                  k0[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k0[3 * i + j])
-                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
-            }
-            if (two) {
-              const double2 G = GA2(q, b + 1);
-              const double gb[3] = {G.x, G.y, G2D(q, b + 1)};
-              s1 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s1)));
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                  k1[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k1[3 * i + j])
-                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
-            }
+              for (int j = 0; j < 3; ++j)
+                k[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k[3 * i + j])
+                                     : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k[3 * i + j]));
           }
           if (RATIO) {
             // A5: lam' / mu' = lambda / mu at every Gauss point, so u_a = rho v_a and with
             // P = sum_q v_a (x) g_b the block is rho P + P^T (+ the diagonal term): 12 instead of 21
             // FMAs per Gauss point and no u in registers
             const double rho = A.rho;
-            const double p01 = k0[1], p02 = k0[2], p12 = k0[5], q01 = k1[1], q02 = k1[2], q12 = k1[5];
-            k0[0] = fma(rho, k0[0], k0[0]);
-            k0[4] = fma(rho, k0[4], k0[4]);
-            k0[8] = fma(rho, k0[8], k0[8]);
-            k0[1] = fma(rho, p01, k0[3]);
-            k0[3] = fma(rho, k0[3], p01);
-            k0[2] = fma(rho, p02, k0[6]);
-            k0[6] = fma(rho, k0[6], p02);
-            k0[5] = fma(rho, p12, k0[7]);
-            k0[7] = fma(rho, k0[7], p12);
-            k1[0] = fma(rho, k1[0], k1[0]);
-            k1[4] = fma(rho, k1[4], k1[4]);
-            k1[8] = fma(rho, k1[8], k1[8]);
-            k1[1] = fma(rho, q01, k1[3]);
-            k1[3] = fma(rho, k1[3], q01);
-            k1[2] = fma(rho, q02, k1[6]);
-            k1[6] = fma(rho, k1[6], q02);
-            k1[5] = fma(rho, q12, k1[7]);
-            k1[7] = fma(rho, k1[7], q12);
+            const double p01 = k[1], p02 = k[2], p12 = k[5];
+            k[0] = fma(rho, k[0], k[0]);
+            k[4] = fma(rho, k[4], k[4]);
+            k[8] = fma(rho, k[8], k[8]);
+            k[1] = fma(rho, p01, k[3]);
+            k[3] = fma(rho, k[3], p01);
+            k[2] = fma(rho, p02, k[6]);
+            k[6] = fma(rho, k[6], p02);
+            k[5] = fma(rho, p12, k[7]);
+            k[7] = fma(rho, k[7], p12);
           }
-          k0[0] += s0;
-          k0[4] += s0;
-          k0[8] += s0;
-          k1[0] += s1;
-          k1[4] += s1;
-          k1[8] += s1;
-          double *dst = kcta + 100 * pr + 9 * ke_pos(a, b);
-          if (two) {
-            double2 *t = tile + lane * 9;
-            t[0] = make_double2(k0[0], k0[1]);
-            t[1] = make_double2(k0[2], k0[3]);
-            t[2] = make_double2(k0[4], k0[5]);
-            t[3] = make_double2(k0[6], k0[7]);
-            t[4] = make_double2(k0[8], k1[0]);
-            t[5] = make_double2(k1[1], k1[2]);
-            t[6] = make_double2(k1[3], k1[4]);
-            t[7] = make_double2(k1[5], k1[6]);
-            t[8] = make_double2(k1[7], k1[8]);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 9; ++it) {
-              const double2 v = tile[it * 32 + lane];
-              const int off = goff[it * 32 + lane];
-              if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + off) = v;
-            }
-            __syncwarp();
-          } else {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
+          k[0] += sd;
+          k[4] += sd;
+          k[8] += sd;
+          const int pos = ke_pos(a, b);   // warp-uniform
+          if (pos == 10) {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
             double2 *t = tile + lane * 5;
-            t[0] = make_double2(k0[0], k0[1]);
-            t[1] = make_double2(k0[2], k0[3]);
-            t[2] = make_double2(k0[4], k0[5]);
-            t[3] = make_double2(k0[6], k0[7]);
-            t[4] = make_double2(k0[8], 0.0);
+            t[0] = make_double2(k[0], k[1]);
+            t[1] = make_double2(k[2], k[3]);
+            t[2] = make_double2(k[4], k[5]);
+            t[3] = make_double2(k[6], k[7]);
+            t[4] = make_double2(k[8], 0.0);
             __syncwarp();
+            double *dst = kcta + 100 * pr + 90;
 #pragma unroll
             for (int it = 0; it < 5; ++it) {
               const int f = it * 32 + lane, le = f / 5;
@@ -417,15 +363,37 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
               if (le < n_here) *reinterpret_cast<double2 *>(dst + le * KE_STRIDE + 2 * (f - 5 * le)) = v;
             }
             __syncwarp();
+          } else if (!(pos & 1)) {   // first block of a pair: doubles 0..8 of the thread's 18
+            double2 *t = tile + lane * 9;
+            t[0] = make_double2(k[0], k[1]);
+            t[1] = make_double2(k[2], k[3]);
+            t[2] = make_double2(k[4], k[5]);
+            t[3] = make_double2(k[6], k[7]);
+            reinterpret_cast<double *>(t)[8] = k[8];
+          } else {                   // second block: doubles 9..17, then the warp stores the pair
+            double2 *t = tile + lane * 9;
+            reinterpret_cast<double *>(t)[9] = k[0];
+            t[5] = make_double2(k[1], k[2]);
+            t[6] = make_double2(k[3], k[4]);
+            t[7] = make_double2(k[5], k[6]);
+            t[8] = make_double2(k[7], k[8]);
+            __syncwarp();
+            double *dst = kcta + 100 * pr + 9 * (pos - 1);
+#pragma unroll
+            for (int it = 0; it < 9; ++it) {
+              const double2 v = tile[it * 32 + lane];
+              const int off = goff[it * 32 + lane];
+              if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + off) = v;
+            }
+            __syncwarp();
           }
         }
       }
   }
 #undef GA2
-#undef TA2
+#undef SG2
 #undef LM2
 #undef G2D
-#undef T2D
 }
 
 }  // namespace fea

@@ -105,8 +105,10 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
     const uint32_t idx = src & 0x7fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
     const size_t off = (size_t)idx * 9 + idx / 11u;
     // 72 bytes at an 8-byte boundary: five 16-byte loads of the enclosing aligned 80 bytes (the
-    // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones --
-    // every load of a lane lands in a different cache line, so L1 tag lookups drop by 9/5
+    // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones: the
+    // 32 lanes of a warp read 32 unrelated blocks, so every load costs 32 L1 sector requests and that
+    // request rate (~1 per clock and SM) is what bounds this kernel.  Three 32-byte LDG.256 of the
+    // enclosing 96 bytes were measured too: no faster (1.97 vs 2.00 ms at best), more data moved.
     const double2 *p = reinterpret_cast<const double2 *>(Ke + (off & ~(size_t)1));
     const bool odd = (off & 1) != 0;
     double w[10];
