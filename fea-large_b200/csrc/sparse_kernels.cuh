@@ -99,6 +99,7 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
   const int base = A.slice_ptr[s];
   const int slot = base + (j << 5) + lane;
   const int k0 = cptr[slot], k1 = cptr[slot + 1];
+  const unsigned f = sflag ? sflag[slot] : 0u;   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int k = k0; k < k1; ++k) {
     const uint32_t src = csrc[k];
@@ -129,14 +130,11 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
       for (int c = 0; c < 9; ++c) acc[c] += v[c];
     }
   }
-  if (sflag) {
-    const unsigned f = sflag[slot];   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
-    if (f & 63u) {
+  if (f & 63u) {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        const int i = c / 3, jj = c % 3;
-        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) acc[c] = 0.0;
-      }
+    for (int c = 0; c < 9; ++c) {
+      const int i = c / 3, jj = c % 3;
+      if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) acc[c] = 0.0;
     }
   }
   double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
