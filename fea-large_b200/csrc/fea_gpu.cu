@@ -69,6 +69,8 @@ struct fea_gpu_ctx {
   fea::Plan plan;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // device->host copy of the residual, overlapped with the K gather
+  cudaEvent_t ev_copy = nullptr;
   ncclComm_t comm = nullptr;
   bool has_comm = false;
   int model = 0, ng = 5;
@@ -227,6 +229,8 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   }
   CU(cudaSetDevice(c->device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 
   try {
     fea::build_plan(c->plan, n_nodes, n_elems, X0, conn, rank, nranks);
@@ -485,6 +489,8 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   }
   if (c->tm_a) cudaEventDestroy(c->tm_a);
   if (c->tm_b) cudaEventDestroy(c->tm_b);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return FEA_GPU_OK;
@@ -1013,25 +1019,32 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
     CU(cudaMemcpyAsync(c->x, c->stage_h, h2d, cudaMemcpyHostToDevice, c->stream));
   }
   TRY(element_pass(c, with_stiffness != 0, true));
-  if (with_stiffness) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
+  // residual first: its way back to the host (copy stream) overlaps the stiffness gather
   phase_begin(c, PH_GATHER_R);
   fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
       c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, c->pflag);   // prescribed rows -> 0 (lambda = 0)
   LAUNCHED();
   phase_end(c, PH_GATHER_R);
   d2h = sizeof(double) * n3;
-  if (c->io_range && c->own_range) {
+  const bool ranged = c->io_range && c->own_range;
+  if (ranged) {
     fea::scatter_nodes_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->own_idx, c->R, c->io_buf);
     LAUNCHED();
-    CU(cudaMemcpyAsync(R + 3 * (size_t)c->own_lo, c->io_buf, d2h, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-  } else {
-    if (!c->stage_h) CU(cudaHostAlloc((void **)&c->stage_h, sizeof(double) * nl3, cudaHostAllocDefault));
-    CU(cudaMemcpyAsync(c->stage_h, c->R, d2h, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+  } else if (!c->stage_h) {
+    CU(cudaHostAlloc((void **)&c->stage_h, sizeof(double) * nl3, cudaHostAllocDefault));
+  }
+  CU(cudaEventRecord(c->ev_copy, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+  if (ranged)
+    CU(cudaMemcpyAsync(R + 3 * (size_t)c->own_lo, c->io_buf, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
+  else
+    CU(cudaMemcpyAsync(c->stage_h, c->R, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (with_stiffness) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
+  CU(cudaStreamSynchronize(c->copy_stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (!ranged)
     for (int32_t l = 0; l < c->n_own; ++l)
       std::memcpy(R + 3 * (size_t)pl.node_gid[(size_t)l], c->stage_h + 3 * (size_t)l, 3 * sizeof(double));
-  }
   if (h2d_bytes) *h2d_bytes = h2d;
   if (d2h_bytes) *d2h_bytes = d2h;
   return FEA_GPU_OK;

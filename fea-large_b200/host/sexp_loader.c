@@ -9,6 +9,10 @@
  */
 #include <ctype.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
@@ -229,25 +233,30 @@ static void read_form(reader *r) { /* '(' already consumed */
 BOOL sexp_data_load(char *filename, fea_task **task, fea_solution_params **fea_params,
                     nodes_array **nodes, elements_array **elements,
                     presc_bnd_array **presc_boundary) {
-  FILE *f = fopen(filename, "rb");
-  long size;
-  char *text;
+  /* The file is mapped, not read: a 50 M-DOF model is a few GB of text, the reader walks it once
+   * front to back and the kernel pages it in (and drops it) behind the cursor. */
+  int fd = open(filename, O_RDONLY);
+  struct stat sb;
+  size_t size;
+  const char *text;
   reader r;
-  if (!f) {
+  if (fd < 0) {
     fprintf(stderr, "Error, could not open file %s\n", filename);   /* :291 */
     return FALSE;
   }
-  fseek(f, 0, SEEK_END);
-  size = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  text = (char *)malloc((size_t)size + 1);
-  if (!text || fread(text, 1, (size_t)size, f) != (size_t)size) {
-    fclose(f);
-    free(text);
+  if (fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+    close(fd);
     printf("Error: unable to parse SEXP input\n");                  /* :298 */
     return FALSE;
   }
-  fclose(f);
+  size = (size_t)sb.st_size;
+  text = (const char *)mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (text == (const char *)MAP_FAILED) {
+    printf("Error: unable to parse SEXP input\n");
+    return FALSE;
+  }
+  madvise((void *)text, size, MADV_SEQUENTIAL);
   memset(&r, 0, sizeof(r));
   r.cur = text;
   r.end = text + size;
@@ -260,7 +269,7 @@ BOOL sexp_data_load(char *filename, fea_task **task, fea_solution_params **fea_p
     fail(&r, "file does not start with (task");
   else
     read_body(&r, NULL);
-  free(text);
+  munmap((void *)text, size);
   if (!r.failed && r.have_solution != 15) fail(&r, "solution form lacks a mandatory attribute");   /* asserts :78-89 */
   if (!r.failed && r.have_model_params != 3) fail(&r, "model-parameters needs :lambda and :mu");      /* asserts :63,66 */
   if (!r.failed && (r.nodes->nodes_count == 0 || r.elements->elements_count == 0)) fail(&r, "no geometry");
