@@ -286,6 +286,7 @@ def main():
     for _ in range(args.warmup):
         step()
     g.sync()
+    g.phase_ms()                    # restart the per-kernel event averages: only timed steps count below
     launches0 = fg.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -307,7 +308,7 @@ def main():
     value = n_elems * args.steps / (ms * 1e-3)
     bad = g.bad_points()
 
-    # per-kernel durations inside the timed loop's configuration (events around each phase of the last step)
+    # per-kernel durations: CUDA events around every launch of the timed steps, averaged (no sync inside the loop)
     elem_ms, gather_ms, gres_ms, bc_ms = ph["element"], ph["gather_k"], ph["gather_r"], ph["bc"]
 
     # ---- end to end: host nodes in, host residual out, every step ---------------------------
@@ -384,6 +385,7 @@ def main():
                 "frac": ach / hbm_peak, "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
                 "algorithmic_bytes_per_element": BYTES_PER_ELEM, "kernel_ms": dom_ms,
+                "kernel_ms_samples": ph.get("phase_samples"),
                 "phase_ms": {"element": elem_ms, "gather_k": gather_ms, "gather_r": gres_ms, "bc": bc_ms}}
     asm_ms = elem_ms + gather_ms + gres_ms
     roofline_fp64 = {"bound": "fp64", "achieved": FLOP_PER_ELEM * cnt["local_elems"] / (asm_ms * 1e-3) / 1e12,

@@ -62,6 +62,7 @@ extern "C" int64_t fea_gpu_launch_count(void) { return g_launches.load(); }
 
 enum { PH_ELEM = 0, PH_GATHER_K, PH_GATHER_R, PH_BC, PH_PCG, PH_SPMV, PH_HALO, PH_COUNT };
 constexpr int SPMV_EVENT_POOL = 128;
+constexpr int PHASE_EVENT_POOL = 32;
 constexpr int MAX_PARTIALS = 4096;
 constexpr size_t FLUSH_BYTES = 512ull << 20;
 
@@ -117,8 +118,10 @@ struct fea_gpu_ctx {
   int32_t *io_idx = nullptr, *own_idx = nullptr;   // local node -> offset inside the range
   double *io_buf = nullptr;
 
-  cudaEvent_t ev_a[PH_COUNT] = {}, ev_b[PH_COUNT] = {};
-  bool ev_set[PH_COUNT] = {};
+  // per phase: a ring of event pairs, one per call since the last fea_gpu_phase_ms (which reports the
+  // average over them: the per-kernel durations of a whole timed region, no sync inside it)
+  cudaEvent_t ev_a[PH_COUNT][PHASE_EVENT_POOL] = {}, ev_b[PH_COUNT][PHASE_EVENT_POOL] = {};
+  int ev_n[PH_COUNT] = {};
   cudaEvent_t sp_a[SPMV_EVENT_POOL] = {}, sp_b[SPMV_EVENT_POOL] = {};
   int sp_used = 0;
   int last_iters = 0;
@@ -171,10 +174,12 @@ static void host_tables(int ng, fea::ElemTables &t) {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-static void phase_begin(fea_gpu_ctx *c, int ph) { cudaEventRecord(c->ev_a[ph], c->stream); }
+static void phase_begin(fea_gpu_ctx *c, int ph) {
+  cudaEventRecord(c->ev_a[ph][c->ev_n[ph] % PHASE_EVENT_POOL], c->stream);
+}
 static void phase_end(fea_gpu_ctx *c, int ph) {
-  cudaEventRecord(c->ev_b[ph], c->stream);
-  c->ev_set[ph] = true;
+  cudaEventRecord(c->ev_b[ph][c->ev_n[ph] % PHASE_EVENT_POOL], c->stream);
+  c->ev_n[ph]++;
 }
 
 // ---------------------------------------------------------------------------------
@@ -414,9 +419,11 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   CU(cudaMemcpyToSymbolAsync(fea::c_tab, &tab, sizeof(tab), 0, cudaMemcpyHostToDevice, c->stream));
 
   for (int i = 0; i < PH_COUNT; ++i) {
-    CU(cudaEventCreate(&c->ev_a[i]));
-    CU(cudaEventCreate(&c->ev_b[i]));
-    c->ev_set[i] = false;
+    for (int k = 0; k < PHASE_EVENT_POOL; ++k) {
+      CU(cudaEventCreate(&c->ev_a[i][k]));
+      CU(cudaEventCreate(&c->ev_b[i][k]));
+    }
+    c->ev_n[i] = 0;
   }
   for (int i = 0; i < SPMV_EVENT_POOL; ++i) {
     CU(cudaEventCreate(&c->sp_a[i]));
@@ -480,8 +487,10 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   for (int i = 0; i < PH_COUNT; ++i) {
-    if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]);
-    if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]);
+    for (int k = 0; k < PHASE_EVENT_POOL; ++k) {
+      if (c->ev_a[i][k]) cudaEventDestroy(c->ev_a[i][k]);
+      if (c->ev_b[i][k]) cudaEventDestroy(c->ev_b[i][k]);
+    }
   }
   for (int i = 0; i < SPMV_EVENT_POOL; ++i) {
     if (c->sp_a[i]) cudaEventDestroy(c->sp_a[i]);
@@ -1085,9 +1094,20 @@ extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
   CU(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 16; ++i) out[i] = 0.0;
   for (int i = 0; i < PH_COUNT; ++i) {
-    if (!c->ev_set[i] || i == PH_SPMV) continue;
-    float f = 0;
-    if (cudaEventElapsedTime(&f, c->ev_a[i], c->ev_b[i]) == cudaSuccess) out[i] = f;
+    if (i == PH_SPMV) continue;
+    const int n = std::min(c->ev_n[i], PHASE_EVENT_POOL);
+    double sum = 0;
+    int got = 0;
+    for (int k = 0; k < n; ++k) {
+      float f = 0;
+      if (cudaEventElapsedTime(&f, c->ev_a[i][k], c->ev_b[i][k]) == cudaSuccess) {
+        sum += f;
+        ++got;
+      }
+    }
+    if (got) out[i] = sum / got;     // average ms per call since the last read
+    if (i == PH_ELEM) out[14] = got;
+    c->ev_n[i] = 0;
   }
   double sp = 0;
   for (int i = 0; i < c->sp_used; ++i) {

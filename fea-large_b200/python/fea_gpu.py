@@ -330,6 +330,7 @@ class FeaGpu:
         _check(lib().fea_gpu_phase_ms(self.h, out))
         keys = ["element", "gather_k", "gather_r", "bc", "pcg", "spmv_avg", "halo"]
         d = dict(zip(keys, (float(v) for v in out)))
+        d["phase_samples"] = int(out[14])
         d["spmv_samples"] = int(out[8])
         d["pcg_iters"] = int(out[9])
         d["pcg_exit"] = int(out[10])

@@ -170,7 +170,9 @@ int64_t fea_gpu_launch_count(void);
 int fea_gpu_timer_start(fea_gpu_handle h);
 int fea_gpu_timer_stop(fea_gpu_handle h, double *ms);
 int fea_gpu_sync(fea_gpu_handle h);
-/* per-phase device time of the most recent call of each phase, ms:
+/* per-phase device time, ms, averaged over the calls of each phase since the previous
+ * fea_gpu_phase_ms (CUDA events around every launch, up to the last 32 calls; reading synchronises
+ * the stream and restarts the averages; [14] = element-pass calls averaged):
  * [0]=element kernel, [1]=matrix gather, [2]=residual gather, [3]=bc,
  * [4]=pcg total, [5]=average in-solve spmv launch, [6]=halo, [8]=spmv launches timed,
  * [9]=pcg iterations, [10]=pcg exit (0 max_iter, 1 tolerance, 2 stall/divergence guard),
