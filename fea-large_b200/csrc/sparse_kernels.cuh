@@ -151,8 +151,10 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 // 9.2 GB; 512 threads 6.9 GB; 1024 threads 4.9 GB -- but fat CTAs lose to drain/launch gaps, while
 // 4 CTAs of 256 threads per slice keep 40 warps per SM on 185 slices: 2.34 -> 2.03 ms.
 // Dealing single columns to a persistent grid (no slice affinity: L1 reuse between the columns of a
-// row is lost and the warps drift apart, 16 GB) and a warp-per-row mapping with lanes over (column,
-// component) (coalesced 72-byte reads, but one 8-byte load in flight per lane) were both slower.
+// row is lost and the warps drift apart, 16 GB) and two warp-per-row mappings with lanes over (column,
+// component) (coalesced 72-byte reads: 3.25 instead of 5 sector requests per block, but ~6x the
+// instructions per contribution and one row's diagonal list, up to 24 deep, serialises its warp)
+// were all slower (profiles/r1b_gather_variants.md).
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
