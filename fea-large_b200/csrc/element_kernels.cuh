@@ -15,8 +15,10 @@
 // registers; its results cross to phase B through shared memory laid out
 // [gauss][field][lane] in 16-byte fields (conflict-free LDS.128/STS.128).  Phase B gives warp
 // w the eleven a<=b blocks of staging region w (rows w and 9-w, fea_plan.hpp) of its lane's
-// element, one block at a time, summed over the Gauss points.  38 doubles per (element, Gauss
-// point) cross over -- 73 KB of shared memory per CTA, three CTAs (15 warps) per SM.
+// element, two consecutive blocks at a time, summed over the Gauss points.  38 doubles per (element,
+// Gauss point) cross over (73 KB of shared memory per CTA); phase B wants ~150 registers, so two
+// CTAs (10 warps) per SM.  (One block at a time under a 128-register cap, three CTAs per SM, was
+// measured too: 1.47 against 1.39 ms.)
 //
 // Closed form used for the tangent (both models):
 //   c^_ikjl = lam' d_ik d_jl + mu' (d_ij d_kl + d_il d_jk)
@@ -82,8 +84,24 @@ __device__ __forceinline__ void inv3(const double (&m)[3][3], double det, double
   o[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
 }
 
-template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO, int OCC>
-__global__ void __launch_bounds__(NG * 32, OCC) element_kernel(ElemArgs A) {
+// A5 with mu != 0: lam' / mu' = lambda / mu at every Gauss point, so u_a = rho v_a and with
+// P = sum_q v_a (x) g_b (accumulated in k) the block is rho P + P^T (+ the diagonal term): 12 instead
+// of 21 FMAs per Gauss point and no u in registers
+__device__ __forceinline__ void ratio_block(double (&k)[9], double rho) {
+  const double p01 = k[1], p02 = k[2], p12 = k[5];
+  k[0] = fma(rho, k[0], k[0]);
+  k[4] = fma(rho, k[4], k[4]);
+  k[8] = fma(rho, k[8], k[8]);
+  k[1] = fma(rho, p01, k[3]);
+  k[3] = fma(rho, k[3], p01);
+  k[2] = fma(rho, p02, k[6]);
+  k[6] = fma(rho, k[6], p02);
+  k[5] = fma(rho, p12, k[7]);
+  k[7] = fma(rho, k[7], p12);
+}
+
+template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO>
+__global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
   double2 *tiles = reinterpret_cast<double2 *>(fld + NG * FLD_DOUBLES);  // [NG][TILE_D2] store tiles
@@ -305,85 +323,84 @@ __global__ void __launch_bounds__(NG * 32, OCC) element_kernel(ElemArgs A) {
           A.Re[(size_t)(3 * a + 1) * A.ne_pad + e] = -r1;
           A.Re[(size_t)(3 * a + 2) * A.ne_pad + e] = -r2;
         }
-        if (!WITH_K) continue;
         // Blocks (a,b), (a,b+1) at an even staging position are 144 contiguous, 16-byte aligned
-        // bytes of K_e.  Each thread drops its block into its row of the warp's tile; once the pair
-        // is there the warp stores it as 16-byte pieces walking those 144-byte chunks with
-        // consecutive lanes.  (v1 stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per
-        // request; v3 transposed but spent ~25 instructions of index arithmetic per 8-byte store,
+        // bytes of K_e.  Each thread drops its pair into its row of the warp's tile and the warp
+        // stores it as 16-byte pieces walking those 144-byte chunks with consecutive lanes.  (v1
+        // stored 8 bytes per lane at a 3960-byte stride: 27 L2 sectors per request; v3 transposed but spent ~25 instructions of index arithmetic per 8-byte store,
         // profiles/r1_v3_ncu_full_summary.md -- here the per-lane offsets come from a table.)
-        for (int b = a; b < 10; ++b) {
-          double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-          double sd = 0.0;
+        if (WITH_K)
+        for (int b = a; b < 10; b += 2) {
+          const bool two = b + 1 < 10;   // warp-uniform
+          double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
-            const double2 G = GA2(q, b);
-            const double gb[3] = {G.x, G.y, G2D(q, b)};
-            sd = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], sd)));
+            {
+              const double2 G = GA2(q, b);
+              const double gb[3] = {G.x, G.y, G2D(q, b)};
+              s0 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s0)));
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+              for (int i = 0; i < 3; ++i)
 #pragma unroll
-              for (int j = 0; j < 3; ++j)
-                k[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k[3 * i + j])
-                                     : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k[3 * i + j]));
+                for (int j = 0; j < 3; ++j)
+                  k0[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k0[3 * i + j])
+                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k0[3 * i + j]));
+            }
+            if (two) {
+              const double2 G = GA2(q, b + 1);
+              const double gb[3] = {G.x, G.y, G2D(q, b + 1)};
+              s1 = fma(ta[q][0], gb[0], fma(ta[q][1], gb[1], fma(ta[q][2], gb[2], s1)));
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  k1[3 * i + j] = RATIO ? fma(va[q][i], gb[j], k1[3 * i + j])
+                                        : fma(ua[q][i], gb[j], fma(va[q][j], gb[i], k1[3 * i + j]));
+            }
           }
           if (RATIO) {
-            // A5: lam' / mu' = lambda / mu at every Gauss point, so u_a = rho v_a and with
-            // P = sum_q v_a (x) g_b the block is rho P + P^T (+ the diagonal term): 12 instead of 21
-            // FMAs per Gauss point and no u in registers
-            const double rho = A.rho;
-            const double p01 = k[1], p02 = k[2], p12 = k[5];
-            k[0] = fma(rho, k[0], k[0]);
-            k[4] = fma(rho, k[4], k[4]);
-            k[8] = fma(rho, k[8], k[8]);
-            k[1] = fma(rho, p01, k[3]);
-            k[3] = fma(rho, k[3], p01);
-            k[2] = fma(rho, p02, k[6]);
-            k[6] = fma(rho, k[6], p02);
-            k[5] = fma(rho, p12, k[7]);
-            k[7] = fma(rho, k[7], p12);
+            ratio_block(k0, A.rho);
+            ratio_block(k1, A.rho);
           }
-          k[0] += sd;
-          k[4] += sd;
-          k[8] += sd;
-          const int pos = ke_pos(a, b);   // warp-uniform
-          if (pos == 10) {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
-            double2 *t = tile + lane * 5;
-            t[0] = make_double2(k[0], k[1]);
-            t[1] = make_double2(k[2], k[3]);
-            t[2] = make_double2(k[4], k[5]);
-            t[3] = make_double2(k[6], k[7]);
-            t[4] = make_double2(k[8], 0.0);
-            __syncwarp();
-            double *dst = kcta + 100 * pr + 90;
-#pragma unroll
-            for (int it = 0; it < 5; ++it) {
-              const int f = it * 32 + lane, le = f / 5;
-              const double2 v = tile[f];
-              if (le < n_here) *reinterpret_cast<double2 *>(dst + le * KE_STRIDE + 2 * (f - 5 * le)) = v;
-            }
-            __syncwarp();
-          } else if (!(pos & 1)) {   // first block of a pair: doubles 0..8 of the thread's 18
+          k0[0] += s0;
+          k0[4] += s0;
+          k0[8] += s0;
+          k1[0] += s1;
+          k1[4] += s1;
+          k1[8] += s1;
+          double *dst = kcta + 100 * pr + 9 * ke_pos(a, b);
+          if (two) {
             double2 *t = tile + lane * 9;
-            t[0] = make_double2(k[0], k[1]);
-            t[1] = make_double2(k[2], k[3]);
-            t[2] = make_double2(k[4], k[5]);
-            t[3] = make_double2(k[6], k[7]);
-            reinterpret_cast<double *>(t)[8] = k[8];
-          } else {                   // second block: doubles 9..17, then the warp stores the pair
-            double2 *t = tile + lane * 9;
-            reinterpret_cast<double *>(t)[9] = k[0];
-            t[5] = make_double2(k[1], k[2]);
-            t[6] = make_double2(k[3], k[4]);
-            t[7] = make_double2(k[5], k[6]);
-            t[8] = make_double2(k[7], k[8]);
+            t[0] = make_double2(k0[0], k0[1]);
+            t[1] = make_double2(k0[2], k0[3]);
+            t[2] = make_double2(k0[4], k0[5]);
+            t[3] = make_double2(k0[6], k0[7]);
+            t[4] = make_double2(k0[8], k1[0]);
+            t[5] = make_double2(k1[1], k1[2]);
+            t[6] = make_double2(k1[3], k1[4]);
+            t[7] = make_double2(k1[5], k1[6]);
+            t[8] = make_double2(k1[7], k1[8]);
             __syncwarp();
-            double *dst = kcta + 100 * pr + 9 * (pos - 1);
 #pragma unroll
             for (int it = 0; it < 9; ++it) {
               const double2 v = tile[it * 32 + lane];
               const int off = goff[it * 32 + lane];
               if ((vmask >> it) & 1u) *reinterpret_cast<double2 *>(dst + off) = v;
+            }
+            __syncwarp();
+          } else {   // the region's last block (a,9): 9 doubles + the pad, 5 double2 per element
+            double2 *t = tile + lane * 5;
+            t[0] = make_double2(k0[0], k0[1]);
+            t[1] = make_double2(k0[2], k0[3]);
+            t[2] = make_double2(k0[4], k0[5]);
+            t[3] = make_double2(k0[6], k0[7]);
+            t[4] = make_double2(k0[8], 0.0);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+              const int f = it * 32 + lane, le = f / 5;
+              const double2 v = tile[f];
+              if (le < n_here) *reinterpret_cast<double2 *>(dst + le * KE_STRIDE + 2 * (f - 5 * le)) = v;
             }
             __syncwarp();
           }

@@ -614,13 +614,13 @@ extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
 // ---------------------------------------------------------------------------------
 // element pass
 
-template <int MODEL, int NG, bool RATIO, int OCC>
-static int launch_element_occ(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
+template <int MODEL, int NG, bool RATIO>
+static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
   const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
   const size_t smem = sizeof(double) * NG * fea::FLD_DOUBLES + sizeof(double2) * NG * fea::TILE_D2 + sizeof(int) * 9 * 32;
 #define FEA_LAUNCH(K, Rr)                                                                          \
   do {                                                                                             \
-    auto kern = fea::element_kernel<MODEL, NG, K, Rr, RATIO, OCC>;                                 \
+    auto kern = fea::element_kernel<MODEL, NG, K, Rr, RATIO>;                                      \
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kern<<<grid, NG * 32, smem, c->stream>>>(args);                                                \
   } while (0)
@@ -631,12 +631,6 @@ static int launch_element_occ(fea_gpu_ctx *c, bool with_k, bool with_r, const fe
 #undef FEA_LAUNCH
   LAUNCHED();
   return FEA_GPU_OK;
-}
-template <int MODEL, int NG, bool RATIO>
-static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
-  // register cap: three CTAs per SM (128 registers) for the A5 ratio form, two (168) for the
-  // two-coefficient form, which would spill at 128 (measured: 1.43 / 1.47 ms against 1.56 ms)
-  return launch_element_occ<MODEL, NG, RATIO, RATIO ? 3 : 2>(c, with_k, with_r, args);
 }
 
 static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
