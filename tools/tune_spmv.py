@@ -15,11 +15,3 @@ print("sell padding:", cnt["sell_slots"] / cnt["nnzb"])
 for rep in range(3):
     ms = g.bench_spmv(50)
     print(f"spmv: {ms:.4f} ms  {bytes_ / ms / 1e6:.0f} GB/s (algorithmic BSR bytes)")
-for rep in range(3):
-    g.assemble_all(True); g.apply_bc(0.0)
-    print({k: round(v, 4) for k, v in g.phase_ms().items() if isinstance(v, float)})
-for gt in (64, 128, 256):
-    g.set_param("gather_threads", gt)
-    for rep in range(2):
-        g.assemble_all(True)
-    print("gather_threads", gt, {k: round(v, 4) for k, v in g.phase_ms().items() if k in ("element", "gather_k")})
