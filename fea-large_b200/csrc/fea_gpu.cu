@@ -71,7 +71,7 @@ struct fea_gpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copy of the residual, overlapped with the K gather
-  cudaEvent_t ev_copy = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   ncclComm_t comm = nullptr;
   bool has_comm = false;
   int model = 0, ng = 5;
@@ -174,11 +174,11 @@ static void host_tables(int ng, fea::ElemTables &t) {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-static void phase_begin(fea_gpu_ctx *c, int ph, cudaStream_t s = nullptr) {
-  cudaEventRecord(c->ev_a[ph][c->ev_n[ph] % PHASE_EVENT_POOL], s ? s : c->stream);
+static void phase_begin(fea_gpu_ctx *c, int ph) {
+  cudaEventRecord(c->ev_a[ph][c->ev_n[ph] % PHASE_EVENT_POOL], c->stream);
 }
-static void phase_end(fea_gpu_ctx *c, int ph, cudaStream_t s = nullptr) {
-  cudaEventRecord(c->ev_b[ph][c->ev_n[ph] % PHASE_EVENT_POOL], s ? s : c->stream);
+static void phase_end(fea_gpu_ctx *c, int ph) {
+  cudaEventRecord(c->ev_b[ph][c->ev_n[ph] % PHASE_EVENT_POOL], c->stream);
   c->ev_n[ph]++;
 }
 
@@ -236,7 +236,6 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
   try {
     fea::build_plan(c->plan, n_nodes, n_elems, X0, conn, rank, nranks);
@@ -500,7 +499,6 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (c->tm_a) cudaEventDestroy(c->tm_a);
   if (c->tm_b) cudaEventDestroy(c->tm_b);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -693,26 +691,12 @@ static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   return FEA_GPU_OK;
 }
 
-// `side`: run on the copy stream, forked after what is on the main stream now (the element pass);
-// the caller joins with join_side().  The residual gather (L1-bound, 0.11 ms) then fills the gaps of
-// the stiffness gather instead of following it.
-static int gather_residual(fea_gpu_ctx *c, const uint8_t *pflag = nullptr, bool side = false) {
-  cudaStream_t s = c->stream;
-  if (side) {
-    CU(cudaEventRecord(c->ev_copy, c->stream));
-    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
-    s = c->copy_stream;
-  }
-  phase_begin(c, PH_GATHER_R, s);
-  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, s>>>(
-      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, pflag);
+static int gather_residual(fea_gpu_ctx *c) {
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, nullptr);
   LAUNCHED();
-  phase_end(c, PH_GATHER_R, s);
-  return FEA_GPU_OK;
-}
-static int join_side(fea_gpu_ctx *c) {
-  CU(cudaEventRecord(c->ev_join, c->copy_stream));
-  CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  phase_end(c, PH_GATHER_R);
   return FEA_GPU_OK;
 }
 
@@ -734,13 +718,16 @@ extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t flags) {
   CHECK_H(c);
   const bool with_k = (flags & FEA_ASSEMBLE_STIFFNESS) != 0, fuse_bc = (flags & FEA_ASSEMBLE_FUSE_BC) != 0;
   TRY(element_pass(c, with_k, true));
-  // solver_apply_prescribed_bc(self, 0) folded into the two gathers (fuse_bc): rows and columns of
-  // prescribed DOFs cancelled keeping the diagonal, their right-hand side rows zero (fea_solver.c:1244-1257)
-  const uint8_t *pf = fuse_bc ? c->pflag : nullptr;
-  if (!with_k) return gather_residual(c, pf);
-  TRY(gather_residual(c, pf, true));
-  TRY(gather_stiffness(c, fuse_bc));
-  return join_side(c);
+  if (with_k) TRY(gather_stiffness(c, fuse_bc));
+  if (!fuse_bc) return gather_residual(c);
+  // solver_apply_prescribed_bc(self, 0) folded into the two gathers: rows and columns of prescribed
+  // DOFs cancelled keeping the diagonal, their right-hand side rows zero (fea_solver.c:1244-1257)
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, c->pflag);
+  LAUNCHED();
+  phase_end(c, PH_GATHER_R);
+  return FEA_GPU_OK;
 }
 
 extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
@@ -1035,18 +1022,26 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
     CU(cudaMemcpyAsync(c->x, c->stage_h, h2d, cudaMemcpyHostToDevice, c->stream));
   }
   TRY(element_pass(c, with_stiffness != 0, true));
-  // the residual gather and its way back to the host run on the copy stream, beside the stiffness gather
-  TRY(gather_residual(c, c->pflag, true));   // prescribed rows -> 0 (lambda = 0)
+  // residual first: its way back to the host (copy stream) overlaps the stiffness gather
+  phase_begin(c, PH_GATHER_R);
+  fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
+      c->n_own, c->rptr, c->rsrc, c->Re, c->ne_pad, c->R, c->pflag);   // prescribed rows -> 0 (lambda = 0)
+  LAUNCHED();
+  phase_end(c, PH_GATHER_R);
   d2h = sizeof(double) * n3;
   const bool ranged = c->io_range && c->own_range;
   if (ranged) {
-    fea::scatter_nodes_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->copy_stream>>>(c->n_own, c->own_idx, c->R, c->io_buf);
+    fea::scatter_nodes_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->own_idx, c->R, c->io_buf);
     LAUNCHED();
-    CU(cudaMemcpyAsync(R + 3 * (size_t)c->own_lo, c->io_buf, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
-  } else {
-    if (!c->stage_h) CU(cudaHostAlloc((void **)&c->stage_h, sizeof(double) * nl3, cudaHostAllocDefault));
-    CU(cudaMemcpyAsync(c->stage_h, c->R, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
+  } else if (!c->stage_h) {
+    CU(cudaHostAlloc((void **)&c->stage_h, sizeof(double) * nl3, cudaHostAllocDefault));
   }
+  CU(cudaEventRecord(c->ev_copy, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+  if (ranged)
+    CU(cudaMemcpyAsync(R + 3 * (size_t)c->own_lo, c->io_buf, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
+  else
+    CU(cudaMemcpyAsync(c->stage_h, c->R, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
   if (with_stiffness) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
   CU(cudaStreamSynchronize(c->copy_stream));
   CU(cudaStreamSynchronize(c->stream));
