@@ -81,9 +81,9 @@ struct fea_gpu_ctx {
   int64_t n_slots = 0;
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
-  int gather_threads = 256;
+  int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
-  int gather_split = 4;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
+  int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;

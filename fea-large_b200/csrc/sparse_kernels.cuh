@@ -149,7 +149,8 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 // there.  Measured on C3 (profiles/r1b_gather_variants.md): one warp per slice (9.5 k slices in
 // flight) read 17.4 GB from DRAM for 7.2 GB of blocks; one 256-thread CTA per slice (740 in flight)
 // 9.2 GB; 512 threads 6.9 GB; 1024 threads 4.9 GB -- but fat CTAs lose to drain/launch gaps, while
-// 4 CTAs of 256 threads per slice keep 40 warps per SM on 185 slices: 2.34 -> 2.03 ms.
+// 4 CTAs of 256 threads per slice keep 40 warps per SM on 185 slices: 2.34 -> 2.03 ms, and 8 CTAs
+// of 128 threads 2.01 ms (the default).
 // Dealing single columns to a persistent grid (no slice affinity: L1 reuse between the columns of a
 // row is lost and the warps drift apart, 16 GB) and two warp-per-row mappings with lanes over (column,
 // component) (coalesced 72-byte reads: 3.25 instead of 5 sector requests per block, but ~6x the
