@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 NOTES = {
     "element_kernel": "shared-memory pipe is the busy unit (column side streams 24 B per block and Gauss point, store tile 2x16 B per value); 10 warps/SM",
-    "gather_blocks_kernel [plain]": "4 CTAs per slice: ~185 slices in flight, their staging stays in L2; bound by L1 sector requests (every lane reads its own 72-byte block)",
+    "gather_blocks_kernel [plain]": "8 CTAs of 128 threads per slice: ~185 slices in flight, their staging stays in L2; bound by L1 sector requests (every lane reads its own 72-byte block)",
     "gather_blocks_kernel [Dirichlet flags folded in]": "what a bench step runs",
     "spmv_sell_kernel": "algorithmic 2.96 GB",
 }
