@@ -27,6 +27,31 @@ TRI = {(a, b): ke_code(a, b) for a in range(10) for b in range(a, 10)}
 assert sorted(TRI.values()) == list(range(55))
 
 
+def test_staging_layout_invariants_the_kernels_rely_on():
+    """K_e staging (fea_plan.hpp): block idx = 55 e + code sits at double offset 9 idx + idx // 11 =
+    500 e + 100 pr + 9 pos.  The element kernel stores block pairs with 16-byte stores and the gather
+    reads the aligned 80-byte window around a block with 16-byte loads: pairs must start on even
+    offsets, blocks must not overlap, and the window must stay inside the element's 500 doubles."""
+    used = np.zeros(500, dtype=int)
+    for (a, b), code in TRI.items():
+        pr, pos = divmod(code, 11)
+        assert pr == min(a, 9 - a)
+        for e in (0, 1, 7, 123456):
+            idx = 55 * e + code
+            assert 9 * idx + idx // 11 == 500 * e + 100 * pr + 9 * pos
+        off = 100 * pr + 9 * pos
+        used[off:off + 9] += 1
+        if pos % 2 == 0:                                   # first block of a pair, or the single at pos 10
+            assert off % 2 == 0
+        if pos < 10 and pos % 2 == 0:                      # its partner follows immediately
+            partner = [ab for ab, c in TRI.items() if c == code + 1]
+            assert partner == [(a, b + 1)]
+        lo = off & ~1
+        assert 0 <= lo and lo + 10 <= 500                  # five double2 loads stay inside the element
+    assert used.max() == 1 and used.sum() == 495           # 55 disjoint blocks, 5 pad doubles
+    assert [i for i in range(500) if not used[i]] == [99, 199, 299, 399, 499]
+
+
 def staged_blocks(o, n_elems):
     """[e][55][3][3] upper-triangular node-pair blocks of the oracle's K_e."""
     out = np.zeros((n_elems, 55, 3, 3))
