@@ -53,21 +53,26 @@ def test_staging_layout_invariants_the_kernels_rely_on():
 
 
 def staged_blocks(o, n_elems):
-    """[e][55][3][3] upper-triangular node-pair blocks of the oracle's K_e."""
-    out = np.zeros((n_elems, 55, 3, 3))
+    """The K_e staging buffer as element_kernel lays it out: [e][500] doubles, block (a<=b) at
+    100 pr + 9 pos (fea_plan.hpp), pad doubles poisoned so that a wrong offset shows."""
+    out = np.full((n_elems, 500), np.nan)
     for e in range(n_elems):
         ke = o.element_matrix(e).reshape(10, 3, 10, 3)
-        for (a, b), t in TRI.items():
-            out[e, t] = ke[a, :, b, :]
+        for (a, b), code in TRI.items():
+            off = 100 * (code // 11) + 9 * (code % 11)
+            out[e, off:off + 9] = ke[a, :, b, :].ravel()
     return out
 
 
 def gather_numpy(plan, staged):
-    """What gather_blocks_kernel computes, in numpy."""
-    flat = staged.reshape(-1, 3, 3)
+    """What gather_blocks_kernel computes, in numpy: block idx = 55 e + code is read at double offset
+    9 idx + idx // 11 of the flat staging buffer."""
+    flat = staged.ravel()
     idx = (plan.csrc & 0x7fffffff).astype(np.int64)
     tr = (plan.csrc >> 31).astype(bool)
-    blocks = flat[idx]
+    off = 9 * idx + idx // 11
+    blocks = flat[off[:, None] + np.arange(9)].reshape(-1, 3, 3)
+    assert np.isfinite(blocks).all()
     blocks[tr] = blocks[tr].transpose(0, 2, 1)
     vals = np.zeros((plan.nnzb, 3, 3))
     np.add.at(vals, np.repeat(np.arange(plan.nnzb), np.diff(plan.cptr)), blocks)
