@@ -368,6 +368,24 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           k1[0] += s1;
           k1[4] += s1;
           k1[8] += s1;
+#if FEA_KE_INTERLEAVED
+          if (live) {
+            double2 *dst2 = reinterpret_cast<double2 *>(A.Ke + (size_t)blockIdx.x * (32 * KE_STRIDE)) +
+                            (size_t)((100 * pr + 9 * ke_pos(a, b)) >> 1) * 32 + lane;
+            dst2[0 * 32] = make_double2(k0[0], k0[1]);
+            dst2[1 * 32] = make_double2(k0[2], k0[3]);
+            dst2[2 * 32] = make_double2(k0[4], k0[5]);
+            dst2[3 * 32] = make_double2(k0[6], k0[7]);
+            dst2[4 * 32] = make_double2(k0[8], two ? k1[0] : 0.0);
+            if (two) {
+              dst2[5 * 32] = make_double2(k1[1], k1[2]);
+              dst2[6 * 32] = make_double2(k1[3], k1[4]);
+              dst2[7 * 32] = make_double2(k1[5], k1[6]);
+              dst2[8 * 32] = make_double2(k1[7], k1[8]);
+            }
+          }
+          continue;
+#endif
           double *dst = kcta + 100 * pr + 9 * ke_pos(a, b);
           if (two) {
             double2 *t = tile + lane * 9;

@@ -388,7 +388,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   const size_t n3 = 3 * (size_t)c->n_own, nl3 = 3 * (size_t)c->n_local;
   TRY(dev_alloc(&c->F_soa, (size_t)c->ng * 9 * c->ne_pad));
   TRY(dev_alloc(&c->S_soa, (size_t)c->ng * 9 * c->ne_pad));
-  TRY(dev_alloc(&c->Ke, (size_t)c->n_elems * fea::KE_STRIDE));
+  TRY(dev_alloc(&c->Ke, (size_t)c->ne_pad * fea::KE_STRIDE));   // ne_pad: whole CTAs of 32 elements
   TRY(dev_alloc(&c->Re, (size_t)30 * c->ne_pad));
   TRY(dev_alloc(&c->vals, (size_t)c->n_slots * 9));
   TRY(dev_alloc(&c->R, n3));

@@ -21,6 +21,13 @@ constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
 // code = 11 pr + pos; the block lives at double offset 500 e + 100 pr + 9 pos = 9 idx + idx / 11
 // with idx = 55 e + code, so every pair starts on a 16-byte boundary (one pad double per region).
 constexpr int KE_STRIDE = 500;          // doubles per element
+// FEA_KE_INTERLEAVED: the 250 16-byte chunks of an element are interleaved across the 32 elements of an
+// element-kernel CTA -- chunk c of element e at double offset ((e / 32) 250 + c) 64 + 2 (e % 32) -- so that
+// the element kernel stores straight from registers (a warp store = 512 contiguous bytes) instead of
+// transposing through shared memory; the gather then reads its five chunks at a 512-byte stride.
+#ifndef FEA_KE_INTERLEAVED
+#define FEA_KE_INTERLEAVED 0
+#endif
 #if defined(__CUDACC__)
 #define FEA_HD __host__ __device__
 #else

@@ -110,6 +110,20 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
     // 32 lanes of a warp read 32 unrelated blocks, so every load costs 32 L1 sector requests and that
     // request rate (~1 per clock and SM) is what bounds this kernel.  Three 32-byte LDG.256 of the
     // enclosing 96 bytes were measured too: no faster (1.97 vs 2.00 ms at best), more data moved.
+#if FEA_KE_INTERLEAVED
+    const uint32_t el = idx / 55u, code = idx - 55u * el, rg = code / 11u;
+    const uint32_t o = 100u * rg + 9u * (code - 11u * rg);       // offset inside the element, doubles
+    const double2 *p = reinterpret_cast<const double2 *>(Ke) + ((size_t)(el >> 5) * 250 + (o >> 1)) * 32 + (el & 31u);
+    const bool odd = (o & 1u) != 0;
+    double w[10];
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const double2 t = p[h * 32];
+      w[2 * h] = t.x;
+      w[2 * h + 1] = t.y;
+    }
+    (void)off;
+#else
     const double2 *p = reinterpret_cast<const double2 *>(Ke + (off & ~(size_t)1));
     const bool odd = (off & 1) != 0;
     double w[10];
@@ -119,6 +133,7 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
       w[2 * h] = t.x;
       w[2 * h + 1] = t.y;
     }
+#endif
     double v[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) v[c] = odd ? w[c + 1] : w[c];

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libfea_gpu.so"))
+# FEA_GPU_LIB: another build of the same library (A/B timing of kernel variants from tools/)
+LIB_PATH = os.environ.get("FEA_GPU_LIB") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libfea_gpu.so"))
 
 MODEL_A5, MODEL_NH = 0, 1
 X0_ZERO, X0_RHS, ABS_TOL = 0, 1, 2
