@@ -79,6 +79,36 @@ def gather_numpy(plan, staged):
     return vals
 
 
+def test_interleaved_staging_variant_addresses_the_same_blocks():
+    """-DFEA_KE_INTERLEAVED=1 (fea_plan.hpp): chunk c (16 bytes) of element e at double offset
+    ((e // 32) * 250 + c) * 64 + 2 * (e % 32).  Writing K_e the way that element kernel does and reading
+    the five chunks around a block the way that gather does must give the same matrix as the flat layout."""
+    m = block_model((3, 2, 2))
+    o = PortOracle(m); o.update_state(); o.assemble_stiffness()
+    p = fg.Plan(m.nodes, m.conn)
+    ne = p.n_elems
+    flat = staged_blocks(o, len(m.conn))[p.elem_gid]                   # [e][500], local element order
+    buf = np.full(((ne + 31) // 32) * 32 * 500, np.nan)
+    e = np.arange(ne)
+    for c in range(250):                                               # the element kernel's stores
+        base = ((e // 32) * 250 + c) * 64 + 2 * (e % 32)
+        buf[base], buf[base + 1] = flat[:, 2 * c], flat[:, 2 * c + 1]
+    idx = (p.csrc & 0x7fffffff).astype(np.int64)
+    el, code = idx // 55, idx % 55
+    off = 100 * (code // 11) + 9 * (code % 11)
+    w = np.empty((len(idx), 10))
+    for h in range(5):                                                 # the gather's five 16-byte loads
+        base = ((el // 32) * 250 + off // 2 + h) * 64 + 2 * (el % 32)
+        w[:, 2 * h], w[:, 2 * h + 1] = buf[base], buf[base + 1]
+    blocks = np.where((off % 2 == 1)[:, None], w[:, 1:10], w[:, 0:9]).reshape(-1, 3, 3)
+    assert np.isfinite(blocks).all()
+    tr = (p.csrc >> 31).astype(bool)
+    blocks[tr] = blocks[tr].transpose(0, 2, 1)
+    vals = np.zeros((p.nnzb, 3, 3))
+    np.add.at(vals, np.repeat(np.arange(p.nnzb), np.diff(p.cptr)), blocks)
+    assert np.array_equal(vals, gather_numpy(p, flat))
+
+
 def bsr_to_dense_rows(plan, vals, n_dof):
     A = np.zeros((3 * plan.n_own, n_dof))
     for I in range(plan.n_own):
