@@ -35,10 +35,10 @@ namespace fea {
 constexpr int ELEMS_PER_CTA = 32;
 // Hand-over fields per Gauss point, [field][lane] (lane-contiguous: conflict-free):
 //   double2 GA[b] = (g0,g1) for the 10 nodes, three double2 of the symmetric
-//   s' = mu' wd I + wd sigma: (s00,s01), (s02,s11), (s12,s22), double2 LM = (lam' wd, mu' wd),
+//   s = wd sigma: (s00,s01), (s02,s11), (s12,s22), double2 LM = (lam' wd, mu' wd),
 //   then plain doubles g2[b].  g = grad N_b in the current configuration, wd = w |det J|.
 // The column side of a block needs only g (24 bytes per Gauss point); the row side forms
-// t_a = s' g_a itself (9 FMAs per Gauss point and row) instead of reading it.
+// t_a = (mu' wd I + s) g_a itself (9 FMAs + 3 adds per Gauss point and row) instead of reading it.
 constexpr int FLD_DOUBLES = 38 * 32;          // doubles per Gauss point
 constexpr int FLD_SG = 10 * 64, FLD_LM = 13 * 64, FLD_G2 = 14 * 64;
 constexpr int TILE_D2 = 9 * 32;               // double2 per warp: the store-transpose tile of one block pair
@@ -47,7 +47,8 @@ struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
   double w[5];          // weights incl. the tetrahedron's 1/6 (:32-54)
 };
-__constant__ ElemTables c_tab;
+// both rules stay resident (index NG == 5): contexts with different n_gauss can be alive on one device
+__constant__ ElemTables c_tabs[2];
 
 struct ElemArgs {
   int n_elems;
@@ -103,6 +104,7 @@ __device__ __forceinline__ void ratio_block(double (&k)[9], double rho) {
 template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO>
 __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  const ElemTables &c_tab = c_tabs[NG == 5 ? 1 : 0];
   double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
   double2 *tiles = reinterpret_cast<double2 *>(fld + NG * FLD_DOUBLES);  // [NG][TILE_D2] store tiles
   int *goff = reinterpret_cast<int *>(tiles + NG * TILE_D2);             // [9][32] store offsets
@@ -260,12 +262,12 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         atomicAdd(A.bad, 1ULL);
     }
 
-    // hand over to phase B: s' = mu' wd I + wd sigma and the scaled coefficients
+    // hand over to phase B: wd sigma and the scaled coefficients
     const double wd = ok ? c_tab.w[gp] * fabs(detJ) : 0.0;  // fabs: fea_solver.c:958,1047,1104
     const double lw = lam1 * wd, mw = mu1 * wd;
-    reinterpret_cast<double2 *>(my + FLD_SG)[lane] = make_double2(ok ? fma(wd, S[0][0], mw) : 0.0, ok ? wd * S[0][1] : 0.0);
-    reinterpret_cast<double2 *>(my + FLD_SG + 64)[lane] = make_double2(ok ? wd * S[0][2] : 0.0, ok ? fma(wd, S[1][1], mw) : 0.0);
-    reinterpret_cast<double2 *>(my + FLD_SG + 128)[lane] = make_double2(ok ? wd * S[1][2] : 0.0, ok ? fma(wd, S[2][2], mw) : 0.0);
+    reinterpret_cast<double2 *>(my + FLD_SG)[lane] = make_double2(ok ? wd * S[0][0] : 0.0, ok ? wd * S[0][1] : 0.0);
+    reinterpret_cast<double2 *>(my + FLD_SG + 64)[lane] = make_double2(ok ? wd * S[0][2] : 0.0, ok ? wd * S[1][1] : 0.0);
+    reinterpret_cast<double2 *>(my + FLD_SG + 128)[lane] = make_double2(ok ? wd * S[1][2] : 0.0, ok ? wd * S[2][2] : 0.0);
     reinterpret_cast<double2 *>(my + FLD_LM)[lane] = make_double2(lw, mw);
   }
   __syncthreads();
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   //   K_ab[i][j] = sum_q  u_ai g_bj + v_aj g_bi + d_ij t_a . g_b,   u = lam' wd g_a, v = mu' wd g_a
   // and the column side streams 24 bytes per Gauss point from shared memory; u, v, t of the row stay
   // in registers (RATIO kernels: A5 with mu != 0, where u = (lambda / mu) v, keep only v and t).
-  // The row's residual R_e[a] = -sum_q (t_a - v_a) (fea_solver.c:1094-1109) falls out of the same loads.
+  // The row's residual R_e[a] = -sum_q wd sigma g_a (fea_solver.c:1094-1109) falls out of the same loads.
 #define GA2(q, b) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + (b)*64)[lane]
 #define SG2(q, h) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_SG + (h)*64)[lane]
 #define LM2(q) reinterpret_cast<const double2 *>(fld + (q)*FLD_DOUBLES + FLD_LM)[lane]
@@ -301,9 +303,11 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           const double g2 = G2D(q, a);
           // explicitly rounded where the compiler could fuse differently from one instantiation to
           // the next: t, v and the residual must not depend on whether K is built in the same pass
-          ta[q][0] = fma(S0.x, G.x, fma(S0.y, G.y, __dmul_rn(S1.x, g2)));
-          ta[q][1] = fma(S0.y, G.x, fma(S1.y, G.y, __dmul_rn(S2.x, g2)));
-          ta[q][2] = fma(S1.x, G.x, fma(S2.x, G.y, __dmul_rn(S2.y, g2)));
+          // wd sigma g_a: the residual integrand itself (fea_solver.c:1094-1109), so R_e carries rounding
+          // of size eps |sigma|, not eps mu' (the two differ by mu / |sigma|, ~1e3 at small strain)
+          const double ts0 = fma(S0.x, G.x, fma(S0.y, G.y, __dmul_rn(S1.x, g2)));
+          const double ts1 = fma(S0.y, G.x, fma(S1.y, G.y, __dmul_rn(S2.x, g2)));
+          const double ts2 = fma(S1.x, G.x, fma(S2.x, G.y, __dmul_rn(S2.y, g2)));
           if (!RATIO) {
             ua[q][0] = LM.x * G.x;
             ua[q][1] = LM.x * G.y;
@@ -312,10 +316,13 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           va[q][0] = __dmul_rn(LM.y, G.x);
           va[q][1] = __dmul_rn(LM.y, G.y);
           va[q][2] = __dmul_rn(LM.y, g2);
+          ta[q][0] = __dadd_rn(ts0, va[q][0]);   // t_a = (mu' wd I + wd sigma) g_a for the d_ij term of K
+          ta[q][1] = __dadd_rn(ts1, va[q][1]);
+          ta[q][2] = __dadd_rn(ts2, va[q][2]);
           if (WITH_R) {
-            r0 = __dadd_rn(r0, __dsub_rn(ta[q][0], va[q][0]));
-            r1 = __dadd_rn(r1, __dsub_rn(ta[q][1], va[q][1]));
-            r2 = __dadd_rn(r2, __dsub_rn(ta[q][2], va[q][2]));
+            r0 = __dadd_rn(r0, ts0);
+            r1 = __dadd_rn(r1, ts1);
+            r2 = __dadd_rn(r2, ts2);
           }
         }
         if (WITH_R && live) {

@@ -72,6 +72,8 @@ struct fea_gpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copy of the residual, overlapped with the K gather
   cudaEvent_t ev_copy = nullptr;
+  cudaStream_t comm_stream = nullptr;   // halo exchange of the CG direction, beside the interior SpMV
+  cudaEvent_t ev_vec = nullptr, ev_halo = nullptr;
   ncclComm_t comm = nullptr;
   bool has_comm = false;
   int model = 0, ng = 5;
@@ -81,9 +83,13 @@ struct fea_gpu_ctx {
   int64_t n_slots = 0;
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
+  int pcg_variant = -1;            // 0 = classic PCG (two reductions), 1 = single reduction, -1 = 1 iff nranks > 1
+  int pcg_overlap = 1;             // halo exchange on its own stream beside the interior SpMV slices
+  int last_exit = 0;               // exit state of the last solve: 0 max_iter, 1 tolerance, 2 stall/divergence guard
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
+  int gather_mode = 9;             // 9 = nine lanes per slot (gather_blocks9_kernel), 1 = lane per slot (gather_blocks_kernel)
 
   double *X0 = nullptr, *x = nullptr;
   int32_t *conn_soa = nullptr;
@@ -93,6 +99,11 @@ struct fea_gpu_ctx {
   uint32_t *csrc = nullptr;
   double *vals = nullptr, *vals_saved = nullptr;
   double *R = nullptr, *u = nullptr, *p = nullptr, *q = nullptr, *r = nullptr, *dinv = nullptr, *u_saved = nullptr;
+  double *pd = nullptr, *sv = nullptr;   // single-reduction PCG: direction p and s = A p (c->p then holds z, c->q holds w)
+  fea::Pcg2State *st2 = nullptr;         // [2] double-buffered state
+  fea::Pcg2State *st2_host = nullptr;
+  int32_t *sl_inner = nullptr, *sl_bound = nullptr;   // SELL slices without / with ghost columns
+  int n_inner = 0, n_bound = 0;
   uint8_t *pflag = nullptr;
   uint8_t *sflag = nullptr;        // [n_slots] bits 0-2 row DOFs prescribed, 3-5 column DOFs, 6 diagonal block
   double *pval = nullptr;
@@ -127,6 +138,7 @@ struct fea_gpu_ctx {
   int last_iters = 0;
   cudaEvent_t tm_a = nullptr, tm_b = nullptr;
   std::vector<int32_t> own_count;  // owned nodes per rank
+  std::vector<int32_t> elem_g2l;   // lazily built: global element id -> local element (-1 = not on this rank)
 };
 
 template <class T>
@@ -187,19 +199,20 @@ static void phase_end(fea_gpu_ctx *c, int ph) {
 // ranks that hold them as ghosts.  Ghosts of one owner are contiguous, so
 // ncclRecv lands in place.
 
-static int halo_exchange(fea_gpu_ctx *c, double *vec) {
+static int halo_exchange(fea_gpu_ctx *c, double *vec, cudaStream_t st = nullptr) {
   const fea::Plan &pl = c->plan;
   if (!c->has_comm || pl.nbr_rank.empty()) return FEA_GPU_OK;
+  if (!st) st = c->stream;
   const int n_send = (int)pl.send_nodes.size();
   if (n_send) {
-    fea::pack_kernel<<<cdiv(3 * (int64_t)n_send, 256), 256, 0, c->stream>>>(n_send, c->send_nodes, vec, c->send_buf);
+    fea::pack_kernel<<<cdiv(3 * (int64_t)n_send, 256), 256, 0, st>>>(n_send, c->send_nodes, vec, c->send_buf);
     LAUNCHED();
   }
   NC(ncclGroupStart());
   for (size_t i = 0; i < pl.nbr_rank.size(); ++i) {
     const int ns = pl.send_ptr[i + 1] - pl.send_ptr[i], nr = pl.recv_ptr[i + 1] - pl.recv_ptr[i];
-    if (ns) NC(ncclSend(c->send_buf + 3 * (size_t)pl.send_ptr[i], 3 * (size_t)ns, ncclDouble, pl.nbr_rank[i], c->comm, c->stream));
-    if (nr) NC(ncclRecv(vec + 3 * ((size_t)c->n_own + pl.recv_ptr[i]), 3 * (size_t)nr, ncclDouble, pl.nbr_rank[i], c->comm, c->stream));
+    if (ns) NC(ncclSend(c->send_buf + 3 * (size_t)pl.send_ptr[i], 3 * (size_t)ns, ncclDouble, pl.nbr_rank[i], c->comm, st));
+    if (nr) NC(ncclRecv(vec + 3 * ((size_t)c->n_own + pl.recv_ptr[i]), 3 * (size_t)nr, ncclDouble, pl.nbr_rank[i], c->comm, st));
   }
   NC(ncclGroupEnd());
   return FEA_GPU_OK;
@@ -236,6 +249,9 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_vec, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
 
   try {
     fea::build_plan(c->plan, n_nodes, n_elems, X0, conn, rank, nranks);
@@ -253,6 +269,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   // tuning knobs for A/B runs of the whole test suite (fea_gpu_set_param does the same per context)
   if (const char *s = getenv("FEA_GATHER_THREADS")) fea_gpu_set_param(c, "gather_threads", atof(s));
   if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
+  if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
     int v = atoi(s);
     if (v >= 1 && v <= 4096) c->pcg_batch = v;
@@ -297,6 +314,21 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_upload(&c->sdiag, pl.sdiag, c->stream));
   TRY(dev_upload(&c->send_nodes, pl.send_nodes, c->stream));
   TRY(dev_alloc(&c->send_buf, 3 * pl.send_nodes.size()));
+  {
+    // slices whose rows reference no ghost column can be multiplied while the halo is still in flight
+    std::vector<int32_t> inner, bound;
+    for (int32_t sl = 0; sl < pl.n_slices; ++sl) {
+      bool ghost = false;
+      for (int32_t k = pl.slice_ptr[(size_t)sl]; k < pl.slice_ptr[(size_t)sl + 1] && !ghost; ++k)
+        ghost = pl.sbcol[(size_t)k] >= pl.n_own;
+      (ghost ? bound : inner).push_back(sl);
+    }
+    c->n_inner = (int)inner.size();
+    c->n_bound = (int)bound.size();
+    TRY(dev_upload(&c->sl_inner, inner, c->stream));
+    TRY(dev_upload(&c->sl_bound, bound, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
 
   // prescribed DOFs: flags for owned+ghost DOFs, summed increments (the reference adds
   // every list entry, fea_solver.c:1210-1240), last value for the RHS (:1256)
@@ -404,6 +436,10 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_alloc(&c->scalar, 4));
   TRY(dev_alloc(&c->bad, 1));
   CU(cudaHostAlloc((void **)&c->ctl_host, sizeof(PcgCtl), cudaHostAllocDefault));
+  std::memset(c->ctl_host, 0, sizeof(PcgCtl));
+  TRY(dev_alloc(&c->st2, 2));
+  CU(cudaHostAlloc((void **)&c->st2_host, sizeof(fea::Pcg2State), cudaHostAllocDefault));
+  std::memset(c->st2_host, 0, sizeof(fea::Pcg2State));
   CU(cudaMemsetAsync(c->F_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
   CU(cudaMemsetAsync(c->S_soa, 0, sizeof(double) * (size_t)c->ng * 9 * c->ne_pad, c->stream));
   CU(cudaMemsetAsync(c->vals, 0, sizeof(double) * (size_t)c->n_slots * 9, c->stream));
@@ -414,9 +450,13 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   CU(cudaMemsetAsync(c->ctl, 0, sizeof(PcgCtl), c->stream));
   CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
 
-  fea::ElemTables tab;
-  host_tables(c->ng, tab);
-  CU(cudaMemcpyToSymbolAsync(fea::c_tab, &tab, sizeof(tab), 0, cudaMemcpyHostToDevice, c->stream));
+  // both quadrature rules, unconditionally: another live context on this device may use the other one
+  for (int k = 0; k < 2; ++k) {
+    fea::ElemTables tab;
+    host_tables(k ? 5 : 4, tab);
+    CU(cudaMemcpyToSymbolAsync(fea::c_tabs, &tab, sizeof(tab), sizeof(tab) * k, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // `tab` is pageable stack memory
+  }
 
   for (int i = 0; i < PH_COUNT; ++i) {
     for (int k = 0; k < PHASE_EVENT_POOL; ++k) {
@@ -481,10 +521,14 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
-                  c->flush, c->export_buf};
+                  c->flush, c->export_buf, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
+  if (c->st2_host) cudaFreeHost(c->st2_host);
+  if (c->ev_vec) cudaEventDestroy(c->ev_vec);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   for (int i = 0; i < PH_COUNT; ++i) {
     for (int k = 0; k < PHASE_EVENT_POOL; ++k) {
@@ -679,6 +723,9 @@ static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   {
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
+    if (c->gather_mode == 9 && !FEA_KE_INTERLEAVED)
+      fea::gather_blocks9_kernel<4, 12><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
+    else
     switch (c->gather_threads) {
       case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
       case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
@@ -743,16 +790,27 @@ extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
 // ---------------------------------------------------------------------------------
 // SpMV / BC / PCG
 
-static int launch_spmv(fea_gpu_ctx *c, const double *x, double *y, bool fuse_dot) {
-  const int grid = std::min(cdiv((int64_t)c->plan.n_slices * 32, 256), MAX_PARTIALS);
-  if (fuse_dot)
-    fea::spmv_sell_kernel<true><<<grid, 256, 0, c->stream>>>(c->plan.n_slices, c->slice_ptr, c->sell_row, c->bcol,
-                                                             c->vals, x, y, c->partials, c->counters + 0, c->ctl);
+// y = K x over all slices, or over the slices of `list`; with `dot_out` the partial of x . y of those rows
+// is reduced (fixed order) into *dot_out and the launch is a no-op once *done_flag is set
+static int launch_spmv_list(fea_gpu_ctx *c, const double *x, double *y, double *dot_out, const int *done_flag,
+                            const int32_t *list, int n_list) {
+  if (n_list <= 0) {
+    if (dot_out) CU(cudaMemsetAsync(dot_out, 0, sizeof(double), c->stream));
+    return FEA_GPU_OK;
+  }
+  const int grid = std::min(cdiv((int64_t)n_list * 32, 256), MAX_PARTIALS);
+  if (dot_out)
+    fea::spmv_sell_kernel<true><<<grid, 256, 0, c->stream>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y,
+                                                             c->partials, c->counters + 0, dot_out, done_flag, list);
   else
-    fea::spmv_sell_kernel<false><<<grid, 256, 0, c->stream>>>(c->plan.n_slices, c->slice_ptr, c->sell_row, c->bcol,
-                                                              c->vals, x, y, c->partials, c->counters + 0, c->ctl);
+    fea::spmv_sell_kernel<false><<<grid, 256, 0, c->stream>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y,
+                                                              c->partials, c->counters + 0, nullptr, nullptr, list);
   LAUNCHED();
   return FEA_GPU_OK;
+}
+static int launch_spmv(fea_gpu_ctx *c, const double *x, double *y, bool fuse_dot) {
+  return launch_spmv_list(c, x, y, fuse_dot ? &c->ctl->pq : nullptr, fuse_dot ? &c->ctl->done : nullptr, nullptr,
+                          c->plan.n_slices);
 }
 
 extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
@@ -793,27 +851,50 @@ extern "C" int fea_gpu_restore_stiffness(fea_gpu_handle c) {
   return FEA_GPU_OK;
 }
 
-extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int32_t flags, int32_t *iters,
-                             double *relres) {
-  CHECK_H(c);
-  if (max_iter < 0 || !(tol >= 0.0)) return FEA_GPU_ERR_ARG;
+static int stall_limit_of(fea_gpu_ctx *c) {
+  // PCG's ||r|| is not monotone; on slender domains it plateaus for O(sqrt(cond)) iterations
+  // (2000+ on a 55x220x55 bar), so the window is generous -- inconsistent singular systems are
+  // caught much earlier by the divergence test in pcg_step_control
+  const double ndof = 3.0 * (double)c->plan.n_nodes_global;
+  return c->pcg_stall > 0 ? c->pcg_stall : std::max(500, (int)(50.0 * std::cbrt(ndof)));
+}
+
+// w = K z with the halo exchange of z hidden behind the slices that need no ghost value
+static int spmv_with_halo(fea_gpu_ctx *c, double *z, double *w, double *dot_a, double *dot_b, const int *done_flag) {
+  const bool timed = c->sp_used < SPMV_EVENT_POOL;
+  if (!c->has_comm || c->plan.nbr_rank.empty() || !c->pcg_overlap || c->n_bound == 0) {
+    TRY(halo_exchange(c, z));
+    if (timed) cudaEventRecord(c->sp_a[c->sp_used], c->stream);
+    TRY(launch_spmv_list(c, z, w, dot_a, done_flag, nullptr, c->plan.n_slices));
+    if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);
+    if (dot_b) CU(cudaMemsetAsync(dot_b, 0, sizeof(double), c->stream));
+    return FEA_GPU_OK;
+  }
+  CU(cudaEventRecord(c->ev_vec, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_vec, 0));
+  TRY(halo_exchange(c, z, c->comm_stream));
+  CU(cudaEventRecord(c->ev_halo, c->comm_stream));
+  if (timed) cudaEventRecord(c->sp_a[c->sp_used], c->stream);
+  TRY(launch_spmv_list(c, z, w, dot_a, done_flag, c->sl_inner, c->n_inner));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  TRY(launch_spmv_list(c, z, w, dot_b, done_flag, c->sl_bound, c->n_bound));
+  if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);   // both parts (and any wait for the halo)
+  return FEA_GPU_OK;
+}
+
+struct SolveExit {
+  int done = 0, iters = 0;
+  double rr_final = 0, bb = 0;
+};
+
+// classic PCG: p.Ap, then r.z and r.r -- two reductions per iteration
+static int solve_classic(fea_gpu_ctx *c, double tol, int32_t max_iter, int32_t flags, SolveExit *ex) {
   const int n = 3 * c->n_own;
   const bool multi = c->has_comm;
   const int abs_tol = (flags & FEA_SOLVE_ABS_TOL) ? 1 : 0;
   const int vgrid = std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS / 4);
-  phase_begin(c, PH_PCG);
-  c->sp_used = 0;
-
-  fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->dinv);
-  LAUNCHED();
-  {
-    // PCG's ||r|| is not monotone; on slender domains it plateaus for O(sqrt(cond)) iterations
-    // (2000+ on a 55x220x55 bar), so the window is generous -- inconsistent singular systems are
-    // caught much earlier by the divergence test in pcg_step_control
-    const double ndof = 3.0 * (double)c->plan.n_nodes_global;
-    const int stall_limit = c->pcg_stall > 0 ? c->pcg_stall : std::max(500, (int)(50.0 * std::cbrt(ndof)));
-    CU(cudaMemcpyAsync(&c->ctl->stall_limit, &stall_limit, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  }
+  const int stall_limit = stall_limit_of(c);
+  CU(cudaMemcpyAsync(&c->ctl->stall_limit, &stall_limit, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (flags & FEA_SOLVE_X0_RHS) {
     CU(cudaMemcpyAsync(c->u, c->R, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     TRY(halo_exchange(c, c->u));
@@ -862,18 +943,109 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
     CU(cudaStreamSynchronize(c->stream));
     done = c->ctl_host->done || launched >= max_iter;
   }
-  double rr_final = c->ctl_host->rr_exit;
-  if (c->ctl_host->done == 2) {   // stalled or diverged: the checkpoint is the answer (see pcg_step_control)
-    CU(cudaMemcpyAsync(c->u, c->u_saved, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    rr_final = c->ctl_host->rr_saved;
+  ex->done = c->ctl_host->done;
+  ex->iters = c->ctl_host->iters;
+  ex->bb = c->ctl_host->bb;
+  ex->rr_final = c->ctl_host->done == 2 ? c->ctl_host->rr_saved : c->ctl_host->rr_exit;
+  return FEA_GPU_OK;
+}
+
+// single-reduction PCG (sparse_kernels.cuh: Pcg2State): z lives in c->p (it needs the ghost range), w in c->q
+static int solve_single_reduction(fea_gpu_ctx *c, double tol, int32_t max_iter, int32_t flags, SolveExit *ex) {
+  const int n = 3 * c->n_own;
+  const bool multi = c->has_comm;
+  const int abs_tol = (flags & FEA_SOLVE_ABS_TOL) ? 1 : 0;
+  const int vgrid = std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS / 4);
+  if (!c->pd) TRY(dev_alloc(&c->pd, (size_t)n));
+  if (!c->sv) TRY(dev_alloc(&c->sv, (size_t)n));
+  fea::Pcg2State *S = c->st2;
+  const double *q0 = nullptr;
+  if (flags & FEA_SOLVE_X0_RHS) {
+    CU(cudaMemcpyAsync(c->u, c->R, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    TRY(halo_exchange(c, c->u));
+    TRY(launch_spmv(c, c->u, c->q, false));
+    q0 = c->q;
+  } else {
+    CU(cudaMemsetAsync(c->u, 0, sizeof(double) * (size_t)n, c->stream));
   }
+  fea::pcg2_init_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->R, q0, c->dinv, c->r, c->p, c->pd, c->sv,
+                                                                   c->partials, c->counters + 1, &S[0]);
+  LAUNCHED();
+  TRY(spmv_with_halo(c, c->p, c->q, &S[0].delta_a, &S[0].delta_b, &S[0].done));
+  if (multi) TRY(allreduce_sum(c, &S[0].gamma, 5));
+  fea::pcg2_finalize_kernel<<<1, 1, 0, c->stream>>>(&S[0], tol, abs_tol, stall_limit_of(c));
+  LAUNCHED();
+  CU(cudaMemcpyAsync(c->u_saved, c->u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+  int launched = 0;
+  bool done = false;
+  while (!done) {
+    const int batch = std::min(c->pcg_batch, max_iter - launched);
+    for (int b = 0; b < batch; ++b) {
+      fea::Pcg2State *Sc = &S[(launched + b) & 1], *Sn = &S[(launched + b + 1) & 1];
+      fea::pcg2_step_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, Sc, Sn, c->p, c->q, c->pd, c->sv, c->u, c->r,
+                                                                       c->dinv, c->u_saved, c->partials, c->counters + 2);
+      LAUNCHED();
+      TRY(spmv_with_halo(c, c->p, c->q, &Sn->delta_a, &Sn->delta_b, &Sn->done));
+      if (multi) TRY(allreduce_sum(c, &Sn->gamma, 4));
+    }
+    launched += batch;
+    CU(cudaMemcpyAsync(c->st2_host, &S[launched & 1], sizeof(fea::Pcg2State), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // the stop test of the iterate just produced runs in the next step: apply it here too, so a solve
+    // that has converged does not queue another batch of no-op iterations
+    done = c->st2_host->done || c->st2_host->rr <= c->st2_host->thresh || launched >= max_iter;
+  }
+  // the state read back is the one the NEXT step would consume: its own stop test has not run yet
+  const fea::Pcg2State &h = *c->st2_host;
+  ex->done = h.done;
+  ex->iters = h.iters;
+  ex->bb = h.bb;
+  ex->rr_final = h.done == 2 ? h.rr_saved : (h.done ? h.rr_exit : h.rr);
+  if (!h.done && h.rr <= h.thresh) ex->done = 1;   // met on the very last permitted iteration
+  // mirror into the classic control block so fea_gpu_phase_ms reports one exit record
+  c->ctl_host->done = ex->done;
+  c->ctl_host->iters = h.iters;
+  c->ctl_host->bb = h.bb;
+  c->ctl_host->best_rr = h.best_rr;
+  c->ctl_host->rr_exit = h.done ? h.rr_exit : h.rr;
+  c->ctl_host->rr_saved = h.rr_saved;
+  c->ctl_host->stall = h.stall;
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int32_t flags, int32_t *iters,
+                             double *relres) {
+  CHECK_H(c);
+  if (max_iter < 0 || !(tol >= 0.0)) return FEA_GPU_ERR_ARG;
+  const int n = 3 * c->n_own;
+  phase_begin(c, PH_PCG);
+  c->sp_used = 0;
+  fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->dinv);
+  LAUNCHED();
+  SolveExit ex;
+  const bool single_reduction = c->pcg_variant < 0 ? c->has_comm : c->pcg_variant == 1;
+  if (single_reduction)
+    TRY(solve_single_reduction(c, tol, max_iter, flags, &ex));
+  else
+    TRY(solve_classic(c, tol, max_iter, flags, &ex));
+  if (ex.done == 2)   // stalled or diverged: the checkpoint is the answer (see pcg_step_control)
+    CU(cudaMemcpyAsync(c->u, c->u_saved, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
   phase_end(c, PH_PCG);
-  c->last_iters = c->ctl_host->iters;
-  if (iters) *iters = c->ctl_host->iters;
-  if (relres) *relres = c->ctl_host->bb > 0.0 ? std::sqrt(rr_final / c->ctl_host->bb) : 0.0;
-  if (!c->ctl_host->done) {
+  c->last_iters = ex.iters;
+  c->last_exit = ex.done;
+  if (iters) *iters = ex.iters;
+  const double rel = ex.bb > 0.0 ? std::sqrt(ex.rr_final / ex.bb) : 0.0;
+  if (relres) *relres = rel;
+  if (!ex.done) {
     g_err = "PCG reached max_iter";
     return FEA_GPU_ERR_NOT_CONVERGED;
+  }
+  if (ex.done == 2 && !(flags & FEA_SOLVE_ACCEPT_STALL)) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "PCG stopped on its stall/divergence guard after %d iterations at relative residual %.3e; "
+             "u holds the best checkpointed iterate", ex.iters, rel);
+    g_err = buf;
+    return FEA_GPU_ERR_STALLED;
   }
   return FEA_GPU_OK;
 }
@@ -934,6 +1106,88 @@ extern "C" int fea_gpu_get_state(fea_gpu_handle c, double *graddefs, double *str
       if (pl.elem_owned[(size_t)e])
         std::memcpy(dst + per * (size_t)pl.elem_gid[(size_t)e], tmp.data() + per * (size_t)e, sizeof(double) * per);
   }
+  return FEA_GPU_OK;
+}
+
+static void ensure_elem_map(fea_gpu_ctx *c) {
+  const fea::Plan &pl = c->plan;
+  if (!c->elem_g2l.empty()) return;
+  c->elem_g2l.assign((size_t)pl.n_elems_global, -1);
+  for (int32_t le = 0; le < pl.n_elems; ++le) c->elem_g2l[(size_t)pl.elem_gid[(size_t)le]] = le;
+}
+
+// graddefs / stresses of a LIST of elements (global ids): what fea_gpu_get_state returns, without moving
+// the tensors of the whole mesh (0.7 GB per million elements).  found[k] = 1 if element k is local to this
+// rank (owned or an interface element it computes redundantly), else its output rows are left untouched.
+extern "C" int fea_gpu_get_state_elems(fea_gpu_handle c, int32_t n, const int32_t *elems, double *graddefs,
+                                       double *stresses, int32_t *found) {
+  CHECK_H(c);
+  if (n < 0 || (n > 0 && !elems)) return FEA_GPU_ERR_ARG;
+  if (n == 0) return FEA_GPU_OK;
+  ensure_elem_map(c);
+  const size_t per = (size_t)c->ng * 9;
+  std::vector<int32_t> le((size_t)n);
+  for (int32_t k = 0; k < n; ++k) {
+    if (elems[k] < 0 || elems[k] >= c->plan.n_elems_global) return FEA_GPU_ERR_ARG;
+    le[(size_t)k] = c->elem_g2l[(size_t)elems[k]];
+    if (found) found[k] = le[(size_t)k] >= 0;
+  }
+  int32_t *dle = nullptr;
+  double *dout = nullptr;
+  std::vector<double> tmp(per * (size_t)n);
+  auto body = [&]() -> int {
+    TRY(dev_alloc(&dle, (size_t)n));
+    TRY(dev_alloc(&dout, per * (size_t)n));
+    CU(cudaMemcpyAsync(dle, le.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    for (int which = 0; which < 2; ++which) {
+      double *dst = which ? stresses : graddefs;
+      if (!dst) continue;
+      fea::state_export_list_kernel<<<cdiv((int64_t)per * n, 256), 256, 0, c->stream>>>(n, dle, c->ne_pad, c->ng,
+                                                                                       which ? c->S_soa : c->F_soa, dout);
+      LAUNCHED();
+      CU(cudaMemcpyAsync(tmp.data(), dout, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      for (int32_t k = 0; k < n; ++k)
+        if (le[(size_t)k] >= 0) std::memcpy(dst + per * (size_t)k, tmp.data() + per * (size_t)k, sizeof(double) * per);
+    }
+    return FEA_GPU_OK;
+  };
+  const int rc = body();
+  cudaFree(dle);
+  cudaFree(dout);
+  return rc;
+}
+
+// Diagnostic read-back of one staged element matrix: what the last element pass with stiffness left in the
+// staging buffer for `element` (global id), expanded from the a <= b block triangle to the dense 30 x 30
+// [3a+i][3b+j] the reference builds in solver_local_constitutive_part + solver_local_initial_stess_part
+// (fea_solver.c:887-1068; compare with the capture at its sp_matrix_element_add call sites).
+extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, double *ke900) {
+  CHECK_H(c);
+  if (!ke900 || element < 0 || element >= c->plan.n_elems_global) return FEA_GPU_ERR_ARG;
+  if (FEA_KE_INTERLEAVED) {
+    g_err = "fea_gpu_get_element_matrix: not available in the interleaved staging build";
+    return FEA_GPU_ERR_ARG;
+  }
+  ensure_elem_map(c);
+  const int32_t le = c->elem_g2l[(size_t)element];
+  if (le < 0) {
+    g_err = "element is not local to this rank";
+    return FEA_GPU_ERR_ARG;
+  }
+  double st[fea::KE_STRIDE];
+  CU(cudaMemcpyAsync(st, c->Ke + (size_t)le * fea::KE_STRIDE, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int a = 0; a < fea::NEN; ++a)
+    for (int b = a; b < fea::NEN; ++b) {
+      const int code = fea::ke_code(a, b);
+      const double *blk = st + 100 * (code / 11) + 9 * (code % 11);
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          ke900[(3 * a + i) * 30 + 3 * b + j] = blk[3 * i + j];
+          ke900[(3 * b + j) * 30 + 3 * a + i] = blk[3 * i + j];
+        }
+    }
   return FEA_GPU_OK;
 }
 
@@ -1128,11 +1382,73 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   if (k == "gather_threads" && (v == 128 || v == 256 || v == 512 || v == 1024)) c->gather_threads = v;
   else if (k == "elem_ratio" && (v == 0 || v == 1)) c->elem_ratio = v != 0;
   else if (k == "gather_split" && v >= 1 && v <= 8) c->gather_split = v;
+  else if (k == "gather_mode" && (v == 1 || v == 9)) c->gather_mode = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
+  else if (k == "pcg_variant" && v >= -1 && v <= 1) c->pcg_variant = v;
+  else if (k == "pcg_overlap" && (v == 0 || v == 1)) c->pcg_overlap = v;
   else {
     g_err = "unknown parameter or value out of range: " + k;
     return FEA_GPU_ERR_ARG;
+  }
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_gpu_measure_dmma(int32_t device, double *dmma_tflops) {
+  if (!dmma_tflops) return FEA_GPU_ERR_ARG;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double *out = nullptr;
+  CU(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  double best = 0;
+  float ms = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(a));
+    fea::dmma_probe_kernel<<<blocks, threads>>>(out, iters);
+    g_launches.fetch_add(1);
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    CU(cudaEventElapsedTime(&ms, a, b));
+    // 8 mma.sync.m8n8k4 per iteration and warp, 8*8*4 FMA each
+    const double tf = 2.0 * 256.0 * 8.0 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *dmma_tflops = best;
+  cudaFree(out);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return FEA_GPU_OK;
+}
+
+// average device time of the two collectives of a PCG iteration, each timed alone on the context's
+// stream: the halo exchange of a [n_local][3] vector and the all-reduce of the four iteration sums
+extern "C" int fea_gpu_bench_comm(fea_gpu_handle c, int32_t reps, double *halo_ms, double *allreduce_ms) {
+  CHECK_H(c);
+  if (reps < 1) return FEA_GPU_ERR_ARG;
+  float ms = 0;
+  if (halo_ms) {
+    TRY(halo_exchange(c, c->p));
+    CU(cudaEventRecord(c->tm_a, c->stream));
+    for (int i = 0; i < reps; ++i) TRY(halo_exchange(c, c->p));
+    CU(cudaEventRecord(c->tm_b, c->stream));
+    CU(cudaEventSynchronize(c->tm_b));
+    CU(cudaEventElapsedTime(&ms, c->tm_a, c->tm_b));
+    *halo_ms = (double)ms / reps;
+  }
+  if (allreduce_ms) {
+    CU(cudaMemsetAsync(c->st2, 0, 2 * sizeof(fea::Pcg2State), c->stream));
+    TRY(allreduce_sum(c, &c->st2[0].gamma, 4));
+    CU(cudaEventRecord(c->tm_a, c->stream));
+    for (int i = 0; i < reps; ++i) TRY(allreduce_sum(c, &c->st2[0].gamma, 4));
+    CU(cudaEventRecord(c->tm_b, c->stream));
+    CU(cudaEventSynchronize(c->tm_b));
+    CU(cudaEventElapsedTime(&ms, c->tm_a, c->tm_b));
+    *allreduce_ms = (double)ms / reps;
   }
   return FEA_GPU_OK;
 }

@@ -1,7 +1,7 @@
 // Host-side planning for the B200 hot path (no CUDA in this file).
 //
-//  * partition: nodes are split into `nranks` contiguous chunks after sorting along the
-//    axis of largest extent (rows of K follow node ownership; an element is
+//  * partition: recursive coordinate bisection of the nodes into `nranks` parts -- slabs for a bar,
+//    boxes for a cube (rows of K follow node ownership; an element is
 //    processed by every rank owning one of its nodes, so owned rows assemble locally).
 //  * symbolic phase: the sparsity pattern the reference obtains dynamically through
 //    sp_matrix_element_add (fea_solver.c:964-969, 1053-1058) -- a full 3x3 block for every
@@ -62,24 +62,43 @@ static MortonBox bounding_box(int32_t n_nodes, const double *X0, double (&hi)[3]
   return b;
 }
 
-// owner[] by equal-count chunks along the longest axis; pos_in_owner[] = Morton rank of the
-// node among its owner's nodes (every rank computes the same two arrays from the global mesh)
-static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nranks, const MortonBox &box,
-                            const double (&hi)[3]) {
+// Recursive coordinate bisection: the node set is cut at the count-median along the axis of its largest
+// extent (ties by id), ranks split in proportion, until every part has one rank.  A bar comes out as slabs
+// along its length, a cube on 8 ranks as 2 x 2 x 2 boxes; any rank count works.
+static void rcb(std::vector<int32_t> &idx, int64_t lo, int64_t hi, int rank0, int nr, const double *X0,
+                std::vector<int32_t> &owner) {
+  if (nr <= 1) {
+    for (int64_t k = lo; k < hi; ++k) owner[(size_t)idx[(size_t)k]] = rank0;
+    return;
+  }
+  double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+  for (int64_t k = lo; k < hi; ++k)
+    for (int d = 0; d < 3; ++d) {
+      const double v = X0[3 * (size_t)idx[(size_t)k] + d];
+      bl[d] = std::min(bl[d], v);
+      bh[d] = std::max(bh[d], v);
+    }
+  // longest axis; on a tie the higher index wins (y before x, as the slab partition of a cube used to cut)
+  int axis = 0;
+  for (int d = 1; d < 3; ++d)
+    if (bh[d] - bl[d] >= bh[axis] - bl[axis]) axis = d;
+  const int nl = nr / 2;
+  const int64_t mid = lo + (hi - lo) * nl / nr;
+  std::sort(idx.begin() + lo, idx.begin() + hi, [&](int32_t a, int32_t b) {
+    const double xa = X0[3 * (size_t)a + axis], xb = X0[3 * (size_t)b + axis];
+    return xa < xb || (xa == xb && a < b);
+  });
+  rcb(idx, lo, mid, rank0, nl, X0, owner);
+  rcb(idx, mid, hi, rank0 + nl, nr - nl, X0, owner);
+}
+
+// owner[] by recursive coordinate bisection; pos_in_owner[] = Morton rank of the node among its
+// owner's nodes (every rank computes the same two arrays from the global mesh)
+static void partition_nodes(Plan &p, int32_t n_nodes, const double *X0, int nranks, const MortonBox &box) {
   p.owner.assign((size_t)n_nodes, 0);
   std::vector<int32_t> order((size_t)n_nodes);
   std::iota(order.begin(), order.end(), 0);
-  if (nranks > 1) {
-    int axis = 0;
-    for (int d = 1; d < 3; ++d)
-      if (hi[d] - box.lo[d] > hi[axis] - box.lo[axis]) axis = d;
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-      double xa = X0[3 * (size_t)a + axis], xb = X0[3 * (size_t)b + axis];
-      return xa < xb || (xa == xb && a < b);
-    });
-    for (int64_t k = 0; k < n_nodes; ++k)
-      p.owner[(size_t)order[(size_t)k]] = (int32_t)(k * nranks / n_nodes);
-  }
+  if (nranks > 1) rcb(order, 0, n_nodes, 0, nranks, X0, p.owner);
   std::vector<uint64_t> key((size_t)n_nodes);
 #pragma omp parallel for schedule(static)
   for (int32_t i = 0; i < n_nodes; ++i) key[(size_t)i] = box.key(X0 + 3 * (size_t)i);
@@ -121,7 +140,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
   p.n_elems_global = n_elems;
   double box_hi[3];
   const MortonBox box = bounding_box(n_nodes, X0, box_hi);
-  partition_nodes(p, n_nodes, X0, nranks, box, box_hi);
+  partition_nodes(p, n_nodes, X0, nranks, box);
   const std::vector<int32_t> &owner = p.owner;
   const std::vector<int32_t> &pos = p.pos_in_owner;
 

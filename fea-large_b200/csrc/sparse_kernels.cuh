@@ -185,6 +185,84 @@ gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, con
   for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, sflag, s, j, lane);
 }
 
+// K3, second mapping: NINE LANES PER SLOT.  The lane-per-slot kernel above makes every warp load touch
+// 32 different 128-byte lines (one block per lane), and ncu pins it on exactly that: L1 tag-stage
+// wavefronts, ~5 per contribution.  Here lane (g, c), g = lane / 9 < 3, c = lane % 9, owns component c of
+// slot 3 r + g in round r = 0..10 of a 32-slot column: one 8-byte load per lane and contribution, the nine
+// lanes of a group read the 72 contiguous bytes of one staged block (1.5 lines on average), and a
+// transposed block is the same load with c -> 3 (c % 3) + c / 3.  The column's gather list is a contiguous
+// range of csrc (slots are list-major), so the warp stages it in shared memory with coalesced loads
+// first: the dependent chain is cptr -> csrc -> K_e once per column, not once per slot.  Sums run in
+// list order exactly as in gather_item (same bits); the finished column leaves through a [9][32] tile so
+// that the stores into the SELL value array stay 256 contiguous bytes per warp.
+constexpr int GATHER9_SRC_CAP = 160;   // list entries staged per column (mean 83 on Kuhn blocks; the rest is read in place)
+
+template <int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
+gather_blocks9_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
+                      const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */) {
+  __shared__ double tile_s[WARPS][9 * 32];
+  __shared__ uint32_t src_s[WARPS][GATHER9_SRC_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x / split, part = blockIdx.x - s * split;
+  if (s >= A.n_slices) return;
+  const int base = A.slice_ptr[s];
+  const int width = (A.slice_ptr[s + 1] - base) >> 5;
+  const int g = lane / 9, c = lane - 9 * g;
+  const int ct = 3 * (c % 3) + c / 3;           // component read from a block stored transposed
+  const int ci = c / 3, cj = c % 3;
+  double *tile = tile_s[warp];
+  uint32_t *srcb = src_s[warp];
+  for (int j = part * WARPS + warp; j < width; j += WARPS * split) {
+    const int slot0 = base + (j << 5);
+    const int cp = cptr[slot0 + lane];
+    const int cend = cptr[slot0 + 32];
+    const int K0 = __shfl_sync(0xffffffffu, cp, 0);
+    const int T = cend - K0;
+    int cpn = __shfl_down_sync(0xffffffffu, cp, 1);
+    if (lane == 31) cpn = cend;
+    for (int i = lane; i < T && i < GATHER9_SRC_CAP; i += 32) srcb[i] = csrc[K0 + i];
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < 11; ++r) {
+      const int sl = 3 * r + g;
+      const bool valid = g < 3 && sl < 32;
+      const int k0 = __shfl_sync(0xffffffffu, cp, sl & 31) - K0;
+      const int k1 = __shfl_sync(0xffffffffu, cpn, sl & 31) - K0;
+      const int n = valid ? k1 - k0 : 0;
+      const int nmax = __reduce_max_sync(0xffffffffu, n);
+      double acc = 0.0;
+      for (int i0 = 0; i0 < nmax; i0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = 0.0;
+          if (i0 + u < n) {
+            const int k = k0 + i0 + u;
+            const uint32_t src = k < GATHER9_SRC_CAP ? srcb[k] : csrc[K0 + k];
+            const uint32_t idx = src & 0x7fffffffu;      // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
+            const size_t off = (size_t)idx * 9 + idx / 11u;
+            v[u] = Ke[off + ((src >> 31) ? ct : c)];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u < n) acc += v[u];
+      }
+      if (valid) {
+        const unsigned f = sflag ? sflag[slot0 + sl] : 0u;   // per-slot Dirichlet flags, see gather_item
+        if ((f & 63u) && (((f >> ci) | (f >> (3 + cj))) & 1u) && !((f & 64u) && ci == cj)) acc = 0.0;
+        tile[c * 32 + sl] = acc;
+      }
+    }
+    __syncwarp();
+    double *out = A.vals + (size_t)slot0 * 9 + lane;
+#pragma unroll
+    for (int c2 = 0; c2 < 9; ++c2) out[c2 * 32] = tile[c2 * 32 + lane];
+    __syncwarp();
+  }
+}
+
 // residual gather: R[3I+i] = sum over (element, a) touching node I of R_e[a][i]
 __global__ void __launch_bounds__(256)
 gather_residual_kernel(int n_rows, const int32_t *__restrict__ rptr, const int32_t *__restrict__ rsrc,
@@ -275,13 +353,15 @@ __global__ void __launch_bounds__(256)
 spmv_sell_kernel(int n_slices, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ sell_row,
                  const int32_t *__restrict__ bcol, const double *__restrict__ vals,
                  const double *__restrict__ x, double *__restrict__ y, double *partials,
-                 unsigned int *counter, PcgCtl *ctl) {
+                 unsigned int *counter, double *dot_out, const int *done_flag,
+                 const int32_t *__restrict__ slice_list /* null: all slices, else n_slices entries */) {
   __shared__ double red[32];
-  if (FUSE_DOT && ctl->done) return;
+  if (FUSE_DOT && *done_flag) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
-  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps_per_grid) {
+  for (int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; si < n_slices; si += warps_per_grid) {
+    const int s = slice_list ? slice_list[si] : si;
     const int base = slice_ptr[s];
     const int width = (slice_ptr[s + 1] - base) >> 5;
     const int row = sell_row[s * 32 + lane];
@@ -308,7 +388,7 @@ spmv_sell_kernel(int n_slices, const int32_t *__restrict__ slice_ptr, const int3
   }
   if (FUSE_DOT) {
     double t[1] = {dot};
-    if (grid_reduce<1>(t, partials, counter, red)) ctl->pq = t[0];
+    if (grid_reduce<1>(t, partials, counter, red)) *dot_out = t[0];
   }
 }
 
@@ -439,6 +519,151 @@ pcg_direction_kernel(int n, const double *__restrict__ r, const double *__restri
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Single-reduction PCG (Chronopoulos & Gear): the recurrences are rearranged so that the three sums
+// of an iteration -- gamma = r.z, delta = w.z (w = A z), r.r -- are all known at the same point, i.e. ONE
+// all-reduce per iteration across ranks instead of two (p.Ap, then r.z / r.r), and one vector kernel
+// instead of two:
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = z + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  z = D^-1 r      (pcg2_step_kernel)
+//     [halo exchange of z]   w = A z, delta = w.z                                     (spmv_sell_kernel)
+//     all-reduce (gamma, delta_a, delta_b, r.r)
+// Same iterates as classic PCG in exact arithmetic (checked: equal iteration counts).  The state is
+// double-buffered: step k reads S[k & 1] (complete) and fills S[(k + 1) & 1], every block re-deriving
+// the same scalars and stop decision from the same inputs, so there is no one-thread control kernel and
+// no block ever reads a field another block of the same launch writes.  Guards as in pcg_step_control.
+
+struct Pcg2State {
+  double gamma, delta_a, delta_b, rr;    // the four all-reduced sums (contiguous), delta split interior / boundary
+  double bb;                             // contiguous with the sums for the 5-double all-reduce of the start
+  double gamma_old, alpha_old;
+  double thresh, best_rr, rr_saved, rr_exit;
+  int done, iters, stall, stall_limit;
+};
+
+// r = b - q (q = A x0) or r = b; z = dinv r; p = s = 0; sums r.z, r.r, b.b into S0
+__global__ void __launch_bounds__(RED_THREADS)
+pcg2_init_kernel(int n, const double *__restrict__ b, const double *__restrict__ q /* null: x0 = 0 */,
+                 const double *__restrict__ dinv, double *__restrict__ r, double *__restrict__ z,
+                 double *__restrict__ p, double *__restrict__ sv, double *partials, unsigned int *counter,
+                 Pcg2State *S0) {
+  __shared__ double red[3 * 32];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double bt = b[t];
+    const double rt = q ? bt - q[t] : bt;
+    const double zt = dinv[t] * rt;
+    r[t] = rt;
+    z[t] = zt;
+    p[t] = 0.0;
+    sv[t] = 0.0;
+    s[0] += rt * zt;
+    s[1] += rt * rt;
+    s[2] += bt * bt;
+  }
+  if (grid_reduce<3>(s, partials, counter, red)) {
+    S0->gamma = s[0];
+    S0->delta_a = 0.0;
+    S0->delta_b = 0.0;
+    S0->rr = s[1];
+    S0->bb = s[2];
+    S0->done = 0;
+  }
+}
+
+// after the (all-reduced) sums of the start are in S0
+__global__ void pcg2_finalize_kernel(Pcg2State *S0, double tol, int abs_tol, int stall_limit) {
+  S0->gamma_old = S0->gamma;
+  S0->alpha_old = 1.0;
+  S0->thresh = abs_tol ? tol * tol : tol * tol * S0->bb;
+  S0->best_rr = S0->rr;
+  S0->rr_saved = S0->rr;
+  S0->rr_exit = S0->rr;
+  S0->iters = 0;
+  S0->stall = 0;
+  S0->stall_limit = stall_limit;
+  S0->done = (S0->bb == 0.0 || S0->rr <= S0->thresh) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+pcg2_step_kernel(int n, const Pcg2State *__restrict__ Sc, Pcg2State *Sn, double *__restrict__ z,
+                 const double *__restrict__ w, double *__restrict__ p, double *__restrict__ sv,
+                 double *__restrict__ x, double *__restrict__ r, const double *__restrict__ dinv,
+                 double *__restrict__ x_saved, double *partials, unsigned int *counter) {
+  __shared__ double red[2 * 32];
+  const Pcg2State c = *Sc;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  if (c.done) {   // queued iterations after the end: carry the final state along
+    if (lead) *Sn = c;
+    return;
+  }
+  int done = 0;
+  const double delta = c.delta_a + c.delta_b;
+  double beta = 0.0, denom = delta;
+  if (c.iters > 0) {
+    beta = c.gamma / c.gamma_old;
+    denom = delta - beta * c.gamma / c.alpha_old;
+  }
+  const double alpha = c.gamma / denom;
+  if (c.rr <= c.thresh) done = 1;
+  else if (!(c.rr == c.rr) || c.rr > 1e14 * c.best_rr || !(denom > 0.0)) done = 2;   // NaN, divergence, breakdown
+  bool save = false;
+  Pcg2State nx = c;
+  nx.rr_exit = c.rr;
+  if (!done) {
+    if (c.rr < 0.5 * c.rr_saved) {
+      nx.rr_saved = c.rr;
+      save = true;
+    }
+    if (c.rr < 0.999 * c.best_rr) {
+      nx.best_rr = c.rr;
+      nx.stall = 0;
+    } else if (++nx.stall >= c.stall_limit) {
+      done = 2;
+      save = false;
+      nx.rr_saved = c.rr_saved;
+    }
+  }
+  nx.done = done;
+  if (done) {
+    if (lead) *Sn = nx;
+    return;
+  }
+  if (lead) {   // everything but the three sums this iteration produces
+    Sn->bb = c.bb;
+    Sn->gamma_old = c.gamma;
+    Sn->alpha_old = alpha;
+    Sn->thresh = c.thresh;
+    Sn->best_rr = nx.best_rr;
+    Sn->rr_saved = nx.rr_saved;
+    Sn->rr_exit = c.rr;
+    Sn->done = 0;
+    Sn->iters = c.iters + 1;
+    Sn->stall = nx.stall;
+    Sn->stall_limit = c.stall_limit;
+  }
+  double s[2] = {0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double pt = fma(beta, p[t], z[t]);
+    const double st = fma(beta, sv[t], w[t]);
+    const double xt = x[t];
+    if (save) x_saved[t] = xt;       // the iterate r.r = c.rr belongs to
+    x[t] = fma(alpha, pt, xt);
+    const double rt = fma(-alpha, st, r[t]);
+    const double zt = dinv[t] * rt;
+    p[t] = pt;
+    sv[t] = st;
+    r[t] = rt;
+    z[t] = zt;
+    s[0] += rt * zt;
+    s[1] += rt * rt;
+  }
+  if (grid_reduce<2>(s, partials, counter, red)) {
+    Sn->gamma = s[0];
+    Sn->rr = s[1];
+  }
+}
+
 // out = a . b (fixed order)
 __global__ void __launch_bounds__(RED_THREADS)
 dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b, double *partials,
@@ -492,6 +717,17 @@ __global__ void state_export_kernel(int n_elems, int ne_pad, int ng, const doubl
   aos[t] = soa[(size_t)f * ne_pad + e];
 }
 
+// the same for a list of local elements (-1 = skip): aos[k][ng][9]
+__global__ void state_export_list_kernel(int n_list, const int32_t *__restrict__ le, int ne_pad, int ng,
+                                         const double *__restrict__ soa, double *__restrict__ aos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)ng * 9;
+  if (t >= (int64_t)n_list * per) return;
+  const int k = (int)(t / per), f = (int)(t - (int64_t)k * per);
+  const int e = le[k];
+  aos[t] = e >= 0 ? soa[(size_t)f * ne_pad + e] : 0.0;
+}
+
 // peak probes -------------------------------------------------------------------
 __global__ void dfma_probe_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -502,6 +738,26 @@ __global__ void dfma_probe_kernel(double *out, int iters) {
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// FP64 tensor-core probe: mma.sync m8n8k4 (256 FMA per warp instruction), eight independent accumulator
+// pairs per warp so the issue rate, not the dependency chain, is measured
+__global__ void dmma_probe_kernel(double *out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = k * 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += c[k][0] + c[k][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
 }
 
 __global__ void copy_probe_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n) {

@@ -393,9 +393,16 @@ BOOL solver_solve_slae(fea_solver_ptr solver) {
   LOGINFO("Starting to solve SLAE");
   rc = fea_gpu_solve(solver->gpu, tol, max_iter, FEA_SOLVE_X0_ZERO, &iters, &solver->last_linear_residual);
   solver->last_linear_iterations = iters;
-  if (rc != FEA_GPU_OK && rc != FEA_GPU_ERR_NOT_CONVERGED) gpu_must(rc, "fea_gpu_solve");
+  if (rc == FEA_GPU_ERR_STALLED)      /* u holds the best checkpointed iterate; the Newton loop goes on with it */
+    LOGERROR("SLAE solver stopped on its stall/divergence guard after %d iterations, relative residual %e (asked %e)",
+             (int)iters, solver->last_linear_residual, tol);
+  else if (rc == FEA_GPU_ERR_NOT_CONVERGED)
+    LOGERROR("SLAE solver reached %d iterations, relative residual %e (asked %e)", max_iter,
+             solver->last_linear_residual, tol);
+  else if (rc != FEA_GPU_OK)
+    gpu_must(rc, "fea_gpu_solve");
   LOGINFO("SLAE solved: %d PCG iterations, relative residual %e", (int)iters, solver->last_linear_residual);
-  return TRUE;
+  return rc == FEA_GPU_OK;
 }
 
 void solver_push_nodes(fea_solver_ptr self) {

@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FEA_GPU_LIB") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libfea_gpu.so"))
 
 MODEL_A5, MODEL_NH = 0, 1
-X0_ZERO, X0_RHS, ABS_TOL = 0, 1, 2
-OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MESH, ERR_NOT_CONVERGED = range(6)
+X0_ZERO, X0_RHS, ABS_TOL, ACCEPT_STALL = 0, 1, 2, 4
+OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MESH, ERR_NOT_CONVERGED, ERR_STALLED = range(7)
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -31,10 +31,10 @@ SYMBOLS = [
     "fea_gpu_update_state", "fea_gpu_assemble_stiffness", "fea_gpu_assemble_residual",
     "fea_gpu_assemble_all", "fea_gpu_apply_bc", "fea_gpu_save_stiffness", "fea_gpu_restore_stiffness",
     "fea_gpu_solve", "fea_gpu_dot_R_u", "fea_gpu_spmv", "fea_gpu_get_state", "fea_gpu_get_forces",
-    "fea_gpu_set_forces", "fea_gpu_get_solution", "fea_gpu_get_csr", "fea_gpu_bad_points",
+    "fea_gpu_set_forces", "fea_gpu_get_solution", "fea_gpu_get_csr", "fea_gpu_get_element_matrix", "fea_gpu_get_state_elems", "fea_gpu_bad_points",
     "fea_gpu_counts", "fea_gpu_launch_count", "fea_gpu_timer_start", "fea_gpu_timer_stop",
     "fea_gpu_sync", "fea_gpu_phase_ms", "fea_gpu_bench_spmv", "fea_gpu_measure_peaks",
-    "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
+    "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_measure_dmma", "fea_gpu_bench_comm", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
     "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_mesh_block", "fea_mesh_cylinder",
 ]
 
@@ -78,6 +78,13 @@ def measure_peaks(device=0):
     a, b = C.c_double(0), C.c_double(0)
     _check(lib().fea_gpu_measure_peaks(int(device), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def measure_dmma(device=0) -> float:
+    a = C.c_double(0)
+    lib().fea_gpu_measure_dmma.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    _check(lib().fea_gpu_measure_dmma(int(device), C.byref(a)))
+    return a.value
 
 
 def mesh_block(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, y0=0.0, bc_style=0, dy=0.0):
@@ -252,12 +259,15 @@ class FeaGpu:
         lib().fea_gpu_apply_bc.argtypes = [C.c_void_p, C.c_double]
         _check(lib().fea_gpu_apply_bc(self.h, float(lam)))
 
-    def solve(self, tol=1e-14, max_iter=20000, flags=X0_ZERO, allow_unconverged=False):
+    def solve(self, tol=1e-14, max_iter=20000, flags=X0_ZERO, allow_unconverged=False, accept_stall=False):
+        """(iterations, relative residual, ok).  A solve that ends on the stall / divergence guard raises
+        (FEA_GPU_ERR_STALLED) unless accept_stall; allow_unconverged returns ok = False instead of raising
+        for both max_iter and the guard."""
         it, rr = C.c_int32(0), C.c_double(0)
         f = lib().fea_gpu_solve
         f.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
-        rc = _check(f(self.h, tol, max_iter, flags, C.byref(it), C.byref(rr)),
-                    allow=(ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        rc = _check(f(self.h, tol, max_iter, flags | (ACCEPT_STALL if accept_stall else 0), C.byref(it), C.byref(rr)),
+                    allow=(ERR_NOT_CONVERGED, ERR_STALLED) if allow_unconverged else ())
         return it.value, rr.value, rc == OK
 
     def dot_R_u(self) -> float:
@@ -299,6 +309,16 @@ class FeaGpu:
         _check(lib().fea_gpu_get_state(self.h, F, S))
         return F, S
 
+    def get_state_elems(self, elems):
+        """F, S [n][ng][3][3] and a mask of the listed (global) elements that are local to this rank."""
+        elems = np.ascontiguousarray(elems, np.int32)
+        F = np.zeros((len(elems), self.ng, 3, 3))
+        S = np.zeros((len(elems), self.ng, 3, 3))
+        found = np.zeros(len(elems), np.int32)
+        lib().fea_gpu_get_state_elems.argtypes = [C.c_void_p, C.c_int32, _ip, _dp, _dp, _ip]
+        _check(lib().fea_gpu_get_state_elems(self.h, len(elems), elems, F, S, found))
+        return F, S, found.astype(bool)
+
     def get_csr(self):
         f = lib().fea_gpu_get_csr
         f.argtypes = [C.c_void_p] * 7
@@ -310,6 +330,16 @@ class FeaGpu:
         v = np.empty(nz.value)
         _check(f(self.h, None, None, rows.ctypes.data, rp.ctypes.data, ci.ctypes.data, v.ctypes.data))
         return rows, rp, ci, v
+
+    def element_matrix(self, e):
+        """Dense 30x30 K_e of global element e from the staging buffer; None if e is not on this rank."""
+        ke = np.zeros((30, 30))
+        lib().fea_gpu_get_element_matrix.argtypes = [C.c_void_p, C.c_int32, _dp]
+        rc = lib().fea_gpu_get_element_matrix(self.h, int(e), ke)
+        if rc == ERR_ARG:
+            return None
+        _check(rc)
+        return ke
 
     def bad_points(self) -> int:
         out = C.c_int64(0)
@@ -348,6 +378,13 @@ class FeaGpu:
         f.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(f(self.h, x, int(with_stiffness), R, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def bench_comm(self, reps=50):
+        """(halo ms, all-reduce ms), each collective timed alone; zeros on one rank."""
+        a, b = C.c_double(0), C.c_double(0)
+        lib().fea_gpu_bench_comm.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _check(lib().fea_gpu_bench_comm(self.h, reps, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def bench_spmv(self, reps=20) -> float:

@@ -33,7 +33,9 @@ enum {
   FEA_GPU_ERR_CUDA = 2,     /* CUDA runtime failure / no device              */
   FEA_GPU_ERR_NCCL = 3,     /* NCCL failure                                  */
   FEA_GPU_ERR_MESH = 4,     /* connectivity out of range, no elements, ...   */
-  FEA_GPU_ERR_NOT_CONVERGED = 5 /* fea_gpu_solve hit max_iter (u is still set) */
+  FEA_GPU_ERR_NOT_CONVERGED = 5, /* fea_gpu_solve hit max_iter (u is still set) */
+  FEA_GPU_ERR_STALLED = 6   /* fea_gpu_solve ended on its stall / divergence guard before reaching
+                               the tolerance; u holds the best checkpointed iterate */
 };
 
 /* model_type, reference fea_model.h:37-40 */
@@ -44,7 +46,9 @@ enum {
   FEA_SOLVE_X0_ZERO = 0,      /* start from u = 0                                        */
   FEA_SOLVE_X0_RHS = 1,       /* start from u = R, as the reference call site does
                                  (fea_solver.c:251-256 passes x0 = b)                    */
-  FEA_SOLVE_ABS_TOL = 2       /* stop on ||r||_2 <= tol instead of ||r||_2 <= tol*||b||_2 */
+  FEA_SOLVE_ABS_TOL = 2,      /* stop on ||r||_2 <= tol instead of ||r||_2 <= tol*||b||_2 */
+  FEA_SOLVE_ACCEPT_STALL = 4  /* a solve that ends on the stall / divergence guard returns FEA_GPU_OK
+                                 (the caller reads `relres`) instead of FEA_GPU_ERR_STALLED */
 };
 
 /* ---- lifetime --------------------------------------------------------- */
@@ -117,8 +121,12 @@ int fea_gpu_restore_stiffness(fea_gpu_handle h);
  * Stops when ||r|| <= tol ||b|| (or tol, FEA_SOLVE_ABS_TOL).  If ||r|| stops improving
  * (rounding floor) or diverges -- K of the reference's "analytical" models is singular, so a
  * noise-level right-hand side is inconsistent -- the solve ends with the checkpointed
- * near-minimum-residual iterate; that is still FEA_GPU_OK and `relres` tells what was reached.
- * iters/relres may be NULL.  Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter. */
+ * near-minimum-residual iterate in u and returns FEA_GPU_ERR_STALLED (FEA_GPU_OK under
+ * FEA_SOLVE_ACCEPT_STALL); `relres` tells what was reached.  iters/relres may be NULL.
+ * Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter.
+ * With nranks > 1 the single-reduction (Chronopoulos-Gear) form of the same iteration runs: one
+ * all-reduce of four doubles per iteration, the halo exchange of the direction overlapped with the
+ * rows that need no ghost value ("pcg_variant" / "pcg_overlap" in fea_gpu_set_param). */
 int fea_gpu_solve(fea_gpu_handle h, double tol, int32_t max_iter, int32_t flags,
                   int32_t *iters, double *relres);
 /* cdot(global_forces_vct, global_solution_vct, n) at :208 */
@@ -131,6 +139,10 @@ int fea_gpu_spmv(fea_gpu_handle h, const double *x, double *y);
 /* graddefs / stresses [n_elems][n_gauss][3][3] (fea_solver.h:262-269).  With
  * nranks>1 only elements owned by this rank are written. */
 int fea_gpu_get_state(fea_gpu_handle h, double *graddefs, double *stresses);
+/* the same for a list of n elements (global ids): graddefs / stresses [n][n_gauss][3][3]; found[k]
+ * (may be NULL) tells whether element k is local to this rank, rows of others are left untouched */
+int fea_gpu_get_state_elems(fea_gpu_handle h, int32_t n, const int32_t *elems, double *graddefs,
+                            double *stresses, int32_t *found);
 int fea_gpu_get_forces(fea_gpu_handle h, double *R);      /* global_forces_vct   */
 int fea_gpu_set_forces(fea_gpu_handle h, const double *R);
 int fea_gpu_get_solution(fea_gpu_handle h, double *u);    /* global_solution_vct */
@@ -139,6 +151,10 @@ int fea_gpu_get_solution(fea_gpu_handle h, double *u);    /* global_solution_vct
  * receives the global DOF id of each returned row. */
 int fea_gpu_get_csr(fea_gpu_handle h, int64_t *n_rows, int64_t *nnz, int32_t *rows,
                     int32_t *rowptr, int32_t *colidx, double *vals);
+/* dense K_e [30][30] (row 3a+i, column 3b+j) of one element, global id, as the last element pass with
+ * stiffness staged it: constitutive + initial-stress part (fea_solver.c:887-1068).  The element must be
+ * local to this rank (FEA_GPU_ERR_ARG otherwise).  Diagnostic / parity checks. */
+int fea_gpu_get_element_matrix(fea_gpu_handle h, int32_t element, double *ke900);
 /* elements whose |J| or det F was <= 0 (or J singular) in the last element pass */
 int fea_gpu_bad_points(fea_gpu_handle h, int64_t *count);
 
@@ -182,7 +198,16 @@ int fea_gpu_phase_ms(fea_gpu_handle h, double out[16]);
 int fea_gpu_bench_spmv(fea_gpu_handle h, int32_t reps, double *ms_per_spmv);
 /* measured machine peaks on this device: FP64 FMA TFLOP/s, copy GB/s (read+write) */
 int fea_gpu_measure_peaks(int32_t device, double *dfma_tflops, double *copy_gbs);
-/* tuning knobs: "pcg_batch" (iterations
+/* FP64 tensor-core peak of this device: mma.sync.m8n8k4.f64 issue rate in TFLOP/s (north_star: DMMA is
+ * used for the element contraction only if it beats the FMA pipe -- this is the measurement) */
+int fea_gpu_measure_dmma(int32_t device, double *dmma_tflops);
+/* average device ms of the two collectives of a PCG iteration, each timed alone (`reps` back to back on
+ * the context's stream): the halo exchange of one [local nodes][3] vector and the all-reduce of the
+ * four iteration sums.  0 when nranks == 1.  Either pointer may be NULL.  Collective. */
+int fea_gpu_bench_comm(fea_gpu_handle h, int32_t reps, double *halo_ms, double *allreduce_ms);
+/* tuning knobs: "gather_mode" (9 = nine lanes per block, the default; 1 = one lane per block),
+ * "pcg_variant" (0 = classic two-reduction PCG, 1 = single-reduction, -1 = automatic: 1 iff nranks > 1),
+ * "pcg_overlap" (1 = halo exchange beside the interior SpMV slices), "pcg_batch" (iterations
  * queued between host convergence checks), "pcg_stall" (iterations without a new best
  * ||r|| before PCG declares the rounding floor; 0 = automatic, max(500, 50 n^(1/3))) */
 int fea_gpu_set_param(fea_gpu_handle h, const char *name, double value);

@@ -1,7 +1,9 @@
 """Run under torchrun on >= 2 GPUs (tests/test_gpu_multirank.py or by hand):
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multirank_worker.py
 Every rank drives its fea_gpu context through a Newton step (NCCL halo exchange + all-reduced
-dots); rank 0 repeats the computation on a single-rank context and on the CPU oracle."""
+dots); rank 0 repeats the computation on a single-rank context and on the CPU oracle.
+bench.py runs the same check (newton_step_check) through its own process group before the timed loop,
+so the driver's 2/4/8-GPU scaling runs carry this evidence too."""
 import os
 import sys
 
@@ -17,19 +19,25 @@ def relmax(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def main():
-    import torch.distributed as dist
+def small_bar(world):
+    """4 x (4 world + 1) x 4 cubes of edge 0.25, clamped ends, Neo-Hookean: every rank gets a slab."""
+    from oracle.kuhn import kuhn_block
+    from oracle.oracle import Model
+    ny = 4 * world + 1
+    mb = kuhn_block(4, ny, 4, 1.0, ny / 4.0, 1.0, 0.0, 1, 0.02)
+    return Model(nodes=mb["nodes"], conn=mb["conn"], presc_node=mb["presc_node"], presc_type=mb["presc_type"],
+                 presc_vals=mb["presc_vals"], model=1, lam=100.0, mu=100.0, gauss=5)
+
+
+def newton_step_check(dist, rank, world, local, log=print):
+    """One Newton step on `world` ranks vs one rank vs the CPU oracle.  Collective; returns
+    (ok, errors) on rank 0 and (True, {}) elsewhere."""
+    import torch
     import fea_gpu as fg
-    from conftest import block_model
     from oracle.oracle import PortOracle
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
     box = [fg.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-
-    ny = 4 * world + 1
-    m = block_model((4, ny, 4), model=1, bc_style=1, dy=0.02, box=(1.0, ny / 4.0, 1.0))   # cubic cells of 0.25
+    m = small_bar(world)
     rng = np.random.default_rng(3)
     x0 = m.nodes + 0.004 * rng.standard_normal(m.nodes.shape)
     g = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals,
@@ -41,24 +49,33 @@ def main():
     g.assemble_all(True)
     R0 = g.get_forces()                      # collective all-gather
     g.apply_bc(0.0)
-    it, rr, ok = g.solve(1e-13, 20000)
-    assert ok and rr <= 1e-13, (it, rr)          # the reported residual must be the converged one on every rank
+    it, rr, ok = g.solve(1e-13, 20000)       # single-reduction PCG, halo overlapped with the interior slices
+    assert ok and rr <= 1e-13, (it, rr)      # the reported residual must be the converged one on every rank
     tol = g.dot_R_u()
     u = g.get_solution()
+    g.set_param("pcg_variant", 0)            # the classic two-reduction recurrences over the same communicator
+    it_c, rr_c, ok_c = g.solve(1e-13, 20000)
+    u_c = g.get_solution()
+    g.set_param("pcg_variant", 1)
+    g.set_param("pcg_overlap", 0)            # and the single-reduction form with the halo in stream order
+    it_n, rr_n, ok_n = g.solve(1e-13, 20000)
+    u_n = g.get_solution()
+    g.set_param("pcg_overlap", 1)
+    g.set_param("pcg_variant", -1)
+    it, rr, ok = g.solve(1e-13, 20000)       # back to the default for the update below
+    assert np.array_equal(g.get_solution(), u), "multi-rank PCG is not bit-reproducible"
     g.update_nodes()                         # x += u, then halo exchange of x
     g.assemble_all(True)
     x1 = g.get_nodes()
     R1 = g.get_forces()
     F, S = g.get_state()                     # only owned elements are written
-    Ssum = np.zeros_like(S)
-    import torch
     t = torch.from_numpy(S.copy()); dist.all_reduce(t); Ssum = t.numpy()   # each element owned once
     # host-buffer step on every rank (each fills its owned rows of the shared-shape host array)
     xh, Rh = fg.host_array(m.nodes.shape), fg.host_array(m.n_dof)
     xh[:] = x1; Rh[:] = 0.0
     g.step_from_host(xh, Rh, True)
     t = torch.from_numpy(np.array(Rh)); dist.all_reduce(t); R_host = t.numpy()
-    status = {"ok": True}
+    good, e = True, {}
     if rank == 0:
         s1 = fg.FeaGpu(m.nodes, m.conn, m.model, m.lam, m.mu, 5, m.presc_node, m.presc_type, m.presc_vals, device=local)
         s1.set_nodes(x0); s1.apply_increment(1.0); s1.assemble_all(True)
@@ -66,6 +83,8 @@ def main():
         s1.apply_bc(0.0)
         it1, rr1, ok1 = s1.solve(1e-13, 20000)
         e["u"] = relmax(u, s1.get_solution())
+        e["u_classic"] = relmax(u_c, s1.get_solution())
+        e["u_no_overlap"] = relmax(u_n, u)
         e["tol"] = abs(tol - s1.dot_R_u()) / abs(tol)
         s1.update_nodes(); s1.assemble_all(True)
         e["x1"] = relmax(x1 - m.nodes, s1.get_nodes() - m.nodes)
@@ -78,14 +97,29 @@ def main():
         e["R0_oracle"] = relmax(R0, o.get_forces())
         o.apply_bc(0.0); o.solve_slae()
         e["u_oracle"] = relmax(u, o.get_solution())
-        print("MULTIRANK", world, "ranks, pcg its", it, it1, "errors", {k: f"{v:.2e}" for k, v in e.items()}, flush=True)
-        good = ok and ok1 and e["R0"] < 1e-12 and e["R1"] < 1e-9 and e["u"] < 1e-9 and e["x1"] < 1e-9 \
-            and e["S"] < 1e-9 and e["R0_oracle"] < 1e-12 and e["u_oracle"] < 1e-9 and e["tol"] < 1e-9 and e["R_hostpath"] < 1e-9
-        status["ok"] = bool(good)
+        log(f"MULTIRANK {world} ranks, pcg its {it} (classic {it_c}, no overlap {it_n}, one rank {it1}) errors "
+            + str({k: f"{v:.2e}" for k, v in e.items()}))
+        good = ok and ok1 and ok_c and ok_n and abs(it - it1) <= max(3, it1 // 50) and abs(it_n - it) <= max(3, it // 50) \
+            and e["R0"] < 1e-12 and e["R1"] < 1e-9 and e["u"] < 1e-9 and e["u_classic"] < 1e-9 \
+            and e["u_no_overlap"] < 1e-9 and e["x1"] < 1e-9 and e["S"] < 1e-9 and e["R0_oracle"] < 1e-12 \
+            and e["u_oracle"] < 1e-9 and e["tol"] < 1e-9 and e["R_hostpath"] < 1e-9
+        e["pcg_iters"] = {"ranks": it, "classic": it_c, "one_rank": it1}
+        s1.close()
+    g.close()
+    return bool(good), e
+
+
+def main():
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    good, _ = newton_step_check(dist, rank, world, local, log=lambda s: print(s, flush=True))
+    if rank == 0:
         print("MULTIRANK_RESULT", "PASS" if good else "FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if status["ok"] else 1)
+    sys.exit(0 if good else 1)
 
 
 if __name__ == "__main__":

@@ -76,7 +76,7 @@ def test_zero_right_hand_side_and_restart_vectors():
     g = make_gpu(m)
     g.assemble_all(True); g.apply_bc(0.0)                 # undeformed: R is rounding noise (F = I to 1e-16)
     assert np.abs(g.get_forces()).max() < 1e-12
-    it, rr, ok = g.solve(1e-14, 5000)
+    it, rr, ok = g.solve(1e-14, 5000, accept_stall=True)   # a noise right-hand side may end on the rounding floor
     assert ok and np.abs(g.get_solution()).max() < 1e-13
     g.set_forces(np.zeros(m.n_dof))                       # an exactly zero right-hand side: nothing to do
     it, rr, ok = g.solve(1e-14, 100)

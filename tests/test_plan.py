@@ -245,3 +245,50 @@ def test_bad_meshes_are_rejected():
     with pytest.raises(fg.FeaGpuError) as e:
         fg.Plan(mb["nodes"], conn)
     assert e.value.code == fg.ERR_MESH
+
+
+def test_rcb_partition_boxes_and_odd_rank_counts():
+    """Recursive coordinate bisection: a cube on 8 ranks becomes 2 x 2 x 2 boxes with up to 7
+    neighbours each, a bar becomes slabs, and rank counts that are not powers of two still balance."""
+    mb = fg.mesh_block(6, 6, 6, 6.0, 6.0, 6.0)
+    nodes, conn = mb["nodes"], mb["conn"]
+    p0 = fg.Plan(nodes, conn, 0, 8)
+    own = p0.owner
+    counts = np.bincount(own, minlength=8)
+    assert counts.min() >= len(nodes) // 8 - 1 and counts.max() <= len(nodes) // 8 + 1
+    for r in range(8):
+        ext = np.ptp(nodes[own == r], axis=0)
+        assert np.all(ext <= 3.5), (r, ext)                     # half the cube in every direction
+    # every rank agrees on the halo: what r sends to q is what q receives from r
+    plans = [p0] + [fg.Plan(nodes, conn, r, 8) for r in range(1, 8)]
+    nbrs = [p.n_nbr for p in plans]       # face, edge and corner neighbours (Kuhn tets couple along one body diagonal only)
+    assert min(nbrs) >= 3 and max(nbrs) == 7, nbrs
+    for r, p in enumerate(plans):
+        for k, q in enumerate(p.nbr_rank):
+            sent = p.node_gid[p.send_nodes[p.send_ptr[k]:p.send_ptr[k + 1]]]
+            pq = plans[q]
+            kk = list(pq.nbr_rank).index(r)
+            recv = pq.node_gid[pq.n_own + pq.recv_ptr[kk]:pq.n_own + pq.recv_ptr[kk + 1]]
+            assert np.array_equal(sent, recv), (r, q)
+    # a bar: slabs along its length, two neighbours at most; three ranks balance to one node
+    mb = fg.mesh_block(2, 9, 2, 2.0, 9.0, 2.0)
+    p = [fg.Plan(mb["nodes"], mb["conn"], r, 3) for r in range(3)]
+    counts = np.bincount(p[0].owner, minlength=3)
+    assert counts.max() - counts.min() <= 1
+    assert [q.n_nbr for q in p] == [1, 2, 1]
+    ymax = [mb["nodes"][p[0].owner == r, 1].max() for r in range(3)]
+    assert ymax[0] <= ymax[1] <= ymax[2]
+
+
+def test_numpy_kuhn_mesher_matches_the_product_mesher():
+    """oracle/kuhn.py (used by bench.py's reference arm and parity window) numbers the block exactly as
+    fea_mesh_block does, windows of a larger block included."""
+    from oracle.kuhn import kuhn_block
+    for args in [(3, 4, 2, 1.0, 2.0, 3.0, 1.0, 0, 0.01), (2, 2, 2, 1.0, 1.0, 1.0, 0.0, 1, 0.02), (3, 2, 4, 3.0, 2.0, 4.0, 0.0, 2, 0.5)]:
+        a, b = fg.mesh_block(*args), kuhn_block(*args)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (args, k)
+    a = fg.mesh_block(5, 7, 4, 5.0, 7.0, 4.0, 0.0, 1, 0.0)
+    w = kuhn_block(2, 3, 2, 5.0, 7.0, 4.0, 0.0, cube_origin=(1, 2, 1), full=(5, 7, 4))
+    assert np.array_equal(a["nodes"][w["node_gid"]], w["nodes"])
+    assert np.array_equal(w["node_gid"][w["conn"]], a["conn"][w["elem_gid"]])
