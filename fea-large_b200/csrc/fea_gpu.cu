@@ -89,9 +89,11 @@ struct fea_gpu_ctx {
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
-  int gather_mode = 9;             // 9 = nine lanes per slot (gather_blocks9_kernel), 1 = lane per slot (gather_blocks_kernel)
+  int gather_mode = 9;             // 9 = nine lanes per block (gather_blocks9_kernel), 1 = lane per slot (gather_blocks_kernel)
+  bool gather9_ok = false;         // the uploaded lists satisfy what gather_blocks9_kernel assumes
 
   double *X0 = nullptr, *x = nullptr;
+  double *x_saved = nullptr;       // fea_gpu_save_nodes (increment control: roll a trial step back)
   int32_t *conn_soa = nullptr;
   double *F_soa = nullptr, *S_soa = nullptr, *Ke = nullptr, *Re = nullptr;
   int32_t *slice_ptr = nullptr, *sell_row = nullptr, *bcol = nullptr, *cptr = nullptr, *rptr = nullptr,
@@ -308,7 +310,30 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_upload(&c->sell_row, pl.sell_row, c->stream));
   TRY(dev_upload(&c->bcol, pl.sbcol, c->stream));
   TRY(dev_upload(&c->cptr, pl.scptr, c->stream));
-  TRY(dev_upload(&c->csrc, pl.scsrc, c->stream));
+  {
+    // device copy of the gather lists: bit 30 marks the last entry of every slot (gather_blocks9_kernel).
+    // That kernel also needs the slots with entries to form a prefix of every 32-slot column (padding only
+    // trails: rows are sorted by length inside a slice) and 30-bit block indices; checked here, once.
+    std::vector<uint32_t> marked(pl.scsrc);
+    bool ok = (int64_t)pl.n_elems * fea::NTRI < (int64_t)fea::SRC_LAST;
+    const int64_t n_cols = pl.n_slots() / fea::SELL_C;
+    for (int64_t col = 0; col < n_cols && ok; ++col) {
+      bool ended = false;
+      for (int l = 0; l < fea::SELL_C; ++l) {
+        const int64_t slot = col * fea::SELL_C + l;
+        const int32_t k0 = pl.scptr[(size_t)slot], k1 = pl.scptr[(size_t)slot + 1];
+        if (k1 > k0) {
+          if (ended) ok = false;
+          marked[(size_t)k1 - 1] |= fea::SRC_LAST;
+        } else {
+          ended = true;
+        }
+      }
+    }
+    c->gather9_ok = ok;
+    TRY(dev_upload(&c->csrc, ok ? marked : pl.scsrc, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   TRY(dev_upload(&c->rptr, pl.rptr, c->stream));
   TRY(dev_upload(&c->rsrc, pl.rsrc, c->stream));
   TRY(dev_upload(&c->sdiag, pl.sdiag, c->stream));
@@ -521,7 +546,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
-                  c->flush, c->export_buf, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
+                  c->flush, c->export_buf, c->x_saved, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -644,14 +669,32 @@ extern "C" int fea_gpu_apply_increment(fea_gpu_handle c, double lambda) {
   return FEA_GPU_OK;
 }
 
-extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) {
+extern "C" int fea_gpu_update_nodes_scaled(fea_gpu_handle c, double eta) {
   CHECK_H(c);
   const int n = 3 * c->n_own;
-  fea::axpy_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, 1.0, c->u, c->x);
+  fea::axpy_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, eta, c->u, c->x);
   LAUNCHED();
   phase_begin(c, PH_HALO);
   TRY(halo_exchange(c, c->x));
   phase_end(c, PH_HALO);
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) { return fea_gpu_update_nodes_scaled(c, 1.0); }
+
+extern "C" int fea_gpu_save_nodes(fea_gpu_handle c) {
+  CHECK_H(c);
+  const size_t nl3 = 3 * (size_t)c->n_local;
+  if (!c->x_saved) TRY(dev_alloc(&c->x_saved, nl3));
+  CU(cudaMemcpyAsync(c->x_saved, c->x, sizeof(double) * nl3, cudaMemcpyDeviceToDevice, c->stream));
+  return FEA_GPU_OK;
+}
+extern "C" int fea_gpu_restore_nodes(fea_gpu_handle c) {
+  CHECK_H(c);
+  if (!c->x_saved) {
+    g_err = "no saved nodes";
+    return FEA_GPU_ERR_ARG;
+  }
+  CU(cudaMemcpyAsync(c->x, c->x_saved, sizeof(double) * 3 * (size_t)c->n_local, cudaMemcpyDeviceToDevice, c->stream));
   return FEA_GPU_OK;
 }
 
@@ -723,8 +766,8 @@ static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   {
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
-    if (c->gather_mode == 9 && !FEA_KE_INTERLEAVED)
-      fea::gather_blocks9_kernel<4, 12><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
+    if (c->gather_mode == 9 && c->gather9_ok && !FEA_KE_INTERLEAVED)
+      fea::gather_blocks9_kernel<4, 10><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
     else
     switch (c->gather_threads) {
       case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
@@ -1313,6 +1356,7 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
 extern "C" int fea_gpu_counts(fea_gpu_handle c, int64_t out[16]) {
   if (!c || !out) return FEA_GPU_ERR_ARG;
   fea::plan_counts(c->plan, out);
+  out[12] = c->gather9_ok ? 1 : 0;
   return FEA_GPU_OK;
 }
 

@@ -103,7 +103,7 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int k = k0; k < k1; ++k) {
     const uint32_t src = csrc[k];
-    const uint32_t idx = src & 0x7fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
+    const uint32_t idx = src & 0x3fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp); bit 30: see SRC_LAST
     const size_t off = (size_t)idx * 9 + idx / 11u;
     // 72 bytes at an 8-byte boundary: five 16-byte loads of the enclosing aligned 80 bytes (the
     // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones: the
@@ -185,80 +185,93 @@ gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, con
   for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, sflag, s, j, lane);
 }
 
-// K3, second mapping: NINE LANES PER SLOT.  The lane-per-slot kernel above makes every warp load touch
-// 32 different 128-byte lines (one block per lane), and ncu pins it on exactly that: L1 tag-stage
-// wavefronts, ~5 per contribution.  Here lane (g, c), g = lane / 9 < 3, c = lane % 9, owns component c of
-// slot 3 r + g in round r = 0..10 of a 32-slot column: one 8-byte load per lane and contribution, the nine
-// lanes of a group read the 72 contiguous bytes of one staged block (1.5 lines on average), and a
-// transposed block is the same load with c -> 3 (c % 3) + c / 3.  The column's gather list is a contiguous
-// range of csrc (slots are list-major), so the warp stages it in shared memory with coalesced loads
-// first: the dependent chain is cptr -> csrc -> K_e once per column, not once per slot.  Sums run in
-// list order exactly as in gather_item (same bits); the finished column leaves through a [9][32] tile so
-// that the stores into the SELL value array stay 256 contiguous bytes per warp.
-constexpr int GATHER9_SRC_CAP = 160;   // list entries staged per column (mean 83 on Kuhn blocks; the rest is read in place)
+// K3, second mapping: NINE LANES PER BLOCK.  The lane-per-slot kernel above makes every 16-byte load of
+// a warp a separate 32-byte sector request (one block per lane): 5.7 sector requests per contribution,
+// and ncu pins it there -- the L1 moves ~1.3 sectors (or shared-memory wavefronts) per clock and SM.
+// Here lane (g, c), g = lane / 9 < 3, c = lane % 9, owns component c, and group g streams the gather
+// lists of slots [11 g, 11 g + 11) of a 32-slot column one contribution after the other: one 8-byte load
+// per lane and contribution, the nine lanes of a group reading the 72 contiguous bytes of one staged
+// block = exactly 3 sectors (a block stored transposed is the same load with c -> 3 (c % 3) + c / 3).  The
+// lists of consecutive slots are consecutive in csrc, so a group walks ONE contiguous range: eight list
+// words per group come in with one 32-byte load and are handed round by shuffles, and the eight block
+// loads that follow are independent.  Bit 30 of a list word marks the last entry of its slot (set when
+// the lists are uploaded), which is all the bookkeeping a contribution needs: add, and on the mark park
+// the sum in a [32][9] tile (lane-contiguous, conflict-free) and start the next slot.  That relies on
+// the slots with entries forming a prefix of every column -- rows are sorted by length inside a slice, so
+// padding only trails; the context checks it when it uploads the lists and keeps the lane-per-slot kernel
+// otherwise.  A slot's sum runs in list order in one register, exactly as in gather_item (same bits).
+// The Dirichlet flags are applied where the column leaves the tile for the SELL value array (lane = slot
+// again: nine coalesced 256-byte stores).
+constexpr int GATHER9_UNROLL = 8;
+constexpr uint32_t SRC_LAST = 0x40000000u;     // device copy of csrc only: last entry of its slot
+constexpr uint32_t SRC_IDX_MASK = 0x3fffffffu;
 
 template <int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 gather_blocks9_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
                       const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */) {
-  __shared__ double tile_s[WARPS][9 * 32];
-  __shared__ uint32_t src_s[WARPS][GATHER9_SRC_CAP];
+  __shared__ double tile_s[WARPS][32 * 9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.x / split, part = blockIdx.x - s * split;
   if (s >= A.n_slices) return;
   const int base = A.slice_ptr[s];
   const int width = (A.slice_ptr[s + 1] - base) >> 5;
   const int g = lane / 9, c = lane - 9 * g;
-  const int ct = 3 * (c % 3) + c / 3;           // component read from a block stored transposed
-  const int ci = c / 3, cj = c % 3;
+  const double *KeC = Ke + c, *KeT = Ke + (3 * (c % 3) + c / 3);   // plain / transposed component of this lane
+  const int s_begin = g < 3 ? 11 * g : 32, s_end = g < 3 ? (g == 2 ? 32 : 11 * g + 11) : 32;
+  const int gl0 = 9 * (g < 3 ? g : 0);          // first lane of this lane's group
+  const uint32_t last_mask = g < 3 ? SRC_LAST : 0u;   // lanes 27..31 only tag along
   double *tile = tile_s[warp];
-  uint32_t *srcb = src_s[warp];
   for (int j = part * WARPS + warp; j < width; j += WARPS * split) {
     const int slot0 = base + (j << 5);
     const int cp = cptr[slot0 + lane];
     const int cend = cptr[slot0 + 32];
-    const int K0 = __shfl_sync(0xffffffffu, cp, 0);
-    const int T = cend - K0;
-    int cpn = __shfl_down_sync(0xffffffffu, cp, 1);
-    if (lane == 31) cpn = cend;
-    for (int i = lane; i < T && i < GATHER9_SRC_CAP; i += 32) srcb[i] = csrc[K0 + i];
+#pragma unroll
+    for (int c2 = 0; c2 < 9; ++c2) tile[c2 * 32 + lane] = 0.0;       // slots without entries stay zero
+    int t = __shfl_sync(0xffffffffu, cp, s_begin & 31);
+    int te = __shfl_sync(0xffffffffu, cp, s_end & 31);
+    if (s_begin == 32) t = cend;
+    if (s_end == 32) te = cend;
+    double *tp = tile + s_begin * 9 + c;       // (never dereferenced by the idle lanes: their range is empty)
+    double acc = 0.0;
+    const int tmax = __reduce_max_sync(0xffffffffu, te - t);
     __syncwarp();
-#pragma unroll 1
-    for (int r = 0; r < 11; ++r) {
-      const int sl = 3 * r + g;
-      const bool valid = g < 3 && sl < 32;
-      const int k0 = __shfl_sync(0xffffffffu, cp, sl & 31) - K0;
-      const int k1 = __shfl_sync(0xffffffffu, cpn, sl & 31) - K0;
-      const int n = valid ? k1 - k0 : 0;
-      const int nmax = __reduce_max_sync(0xffffffffu, n);
-      double acc = 0.0;
-      for (int i0 = 0; i0 < nmax; i0 += 4) {
-        double v[4];
+    for (int it = 0; it < tmax; it += GATHER9_UNROLL, t += GATHER9_UNROLL) {
+      // lanes c < 8 of a group fetch its next eight list words (one sector), everyone gets them by shuffle
+      uint32_t mine = 0u;
+      if (c < GATHER9_UNROLL && t + c < te) mine = csrc[t + c];
+      uint32_t src[GATHER9_UNROLL];
+      double v[GATHER9_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = 0.0;
-          if (i0 + u < n) {
-            const int k = k0 + i0 + u;
-            const uint32_t src = k < GATHER9_SRC_CAP ? srcb[k] : csrc[K0 + k];
-            const uint32_t idx = src & 0x7fffffffu;      // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
-            const size_t off = (size_t)idx * 9 + idx / 11u;
-            v[u] = Ke[off + ((src >> 31) ? ct : c)];
-          }
-        }
+      for (int u = 0; u < GATHER9_UNROLL; ++u) src[u] = __shfl_sync(0xffffffffu, mine, gl0 + u);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (i0 + u < n) acc += v[u];
+      for (int u = 0; u < GATHER9_UNROLL; ++u) {
+        const uint32_t idx = src[u] & SRC_IDX_MASK;        // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
+        const size_t off = (size_t)idx * 9 + idx / 11u;
+        v[u] = 0.0;
+        if (t + u < te) v[u] = ((src[u] >> 31) ? KeT : KeC)[off];
       }
-      if (valid) {
-        const unsigned f = sflag ? sflag[slot0 + sl] : 0u;   // per-slot Dirichlet flags, see gather_item
-        if ((f & 63u) && (((f >> ci) | (f >> (3 + cj))) & 1u) && !((f & 64u) && ci == cj)) acc = 0.0;
-        tile[c * 32 + sl] = acc;
+#pragma unroll
+      for (int u = 0; u < GATHER9_UNROLL; ++u) {
+        acc += v[u];                             // beyond the range v = 0 and no mark: harmless
+        if (src[u] & last_mask) {
+          *tp = acc;
+          tp += 9;
+          acc = 0.0;
+        }
       }
     }
     __syncwarp();
+    // lane = slot from here: Dirichlet flags, then nine coalesced stores
+    const unsigned f = sflag ? sflag[slot0 + lane] : 0u;   // per-slot flags, see gather_item
     double *out = A.vals + (size_t)slot0 * 9 + lane;
 #pragma unroll
-    for (int c2 = 0; c2 < 9; ++c2) out[c2 * 32] = tile[c2 * 32 + lane];
+    for (int c2 = 0; c2 < 9; ++c2) {
+      double a = tile[lane * 9 + c2];
+      const int i = c2 / 3, jj = c2 % 3;
+      if ((f & 63u) && (((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) a = 0.0;
+      out[c2 * 32] = a;
+    }
     __syncwarp();
   }
 }

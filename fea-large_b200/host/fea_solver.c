@@ -119,46 +119,118 @@ int do_main(char *filename) {
  * on the same coordinates (stresses at the end of an iteration :217-218, residual :185 and,
  * for full Newton, stiffness :200 at the start of the next) are one fused device pass here. */
 
+/* Golden-section search of the step length along the Newton direction, as the reference's prototype does
+ * when :line-search :max is positive (solver-prototype/cartesian3d/large/cartesian3d_large.m:85-119):
+ * minimise f(eta) = |eta <u, R(x + eta u)>| on [0.5, 1]; if both probes are worse than the plain Newton
+ * value |<u, R(x)>| the full step is kept.  The shipped solver-large parses the key and never reads it
+ * (fea_solver.h:105, sexp_loader.c:153-167); all shipped models say 0, which leaves solve() as it was. */
+static real solver_line_search(fea_solver_ptr solver, real tolerance, int max_iter) {
+  const real tau = (sqrt(5.0) - 1.0) / 2.0;
+  real a = 0.5, b = 1.0, eta = 1.0;
+  int it;
+  for (it = 0; it < max_iter; ++it) {
+    const real x1 = b - tau * (b - a), x2 = a + tau * (b - a);
+    real f1, f2;
+    gpu_must(fea_gpu_restore_nodes(solver->gpu), "fea_gpu_restore_nodes");
+    gpu_must(fea_gpu_update_nodes_scaled(solver->gpu, x1), "fea_gpu_update_nodes_scaled");
+    gpu_must(fea_gpu_assemble_all(solver->gpu, FEA_ASSEMBLE_FUSE_BC), "fea_gpu_assemble_all");   /* R only, BC rows zero */
+    gpu_must(fea_gpu_dot_R_u(solver->gpu, &f1), "fea_gpu_dot_R_u");
+    f1 = fabs(x1 * f1);
+    gpu_must(fea_gpu_restore_nodes(solver->gpu), "fea_gpu_restore_nodes");
+    gpu_must(fea_gpu_update_nodes_scaled(solver->gpu, x2), "fea_gpu_update_nodes_scaled");
+    gpu_must(fea_gpu_assemble_all(solver->gpu, FEA_ASSEMBLE_FUSE_BC), "fea_gpu_assemble_all");
+    gpu_must(fea_gpu_dot_R_u(solver->gpu, &f2), "fea_gpu_dot_R_u");
+    f2 = fabs(x2 * f2);
+    LOG("Line search: f(%f) = %e, f(%f) = %e", x1, f1, x2, f2);
+    if (f1 > f2) a = x1; else b = x2;
+    if (fabs(tolerance) < f1 && fabs(tolerance) < f2) {
+      eta = 1.0;
+      break;
+    }
+    eta = (x1 + x2) / 2.0;
+  }
+  gpu_must(fea_gpu_restore_nodes(solver->gpu), "fea_gpu_restore_nodes");
+  return eta;
+}
+
 void solve(fea_task_ptr task, fea_solution_params_ptr fea_params, nodes_array_ptr nodes,
            elements_array_ptr elements, presc_bnd_array_ptr presc_boundary) {
   fea_solver_ptr solver = fea_solver_alloc(task, fea_params, nodes, elements, presc_boundary);
   int it = 0;
   real tolerance;
+  const char *keep = getenv("FEA_KEEP_STEPS");
+  /* FEA_KEEP_STEPS=0: no host snapshot per increment (9.5 GB each at 50 M DOF); only the last state is pulled
+   * for the exporter.  Default: every increment, as the reference (fea_solver.c:233, :605-636). */
+  const BOOL keep_steps = !(keep && atoi(keep) == 0);
   LOG("Create elements database");
   solver_create_element_database(solver);
   LOG("Create an array of shape functions gradients in initial configuration");
   solver_create_initial_shape_gradients(solver);
 
   for (; solver->current_load_step < task->load_increments_count; ++solver->current_load_step) {
-    it = 0;
-    solver_update_nodes_with_bc(solver, 1);                    /* full value every increment, :168 */
-    /* :171-179: gradients, stresses, K, keep K for modified Newton; the residual of the first
-     * iteration (:185) comes out of the same element pass */
-    gpu_must(fea_gpu_assemble_all(solver->gpu, 1), "fea_gpu_assemble_all");
-    gpu_must(fea_gpu_save_stiffness(solver->gpu), "fea_gpu_save_stiffness");
-    do {
-      it++;
-      if (it > 1) {
-        /* state of the updated nodes + residual (+ K for full Newton) in one pass */
-        gpu_must(fea_gpu_assemble_all(solver->gpu, task->modified_newton ? 0 : 1), "fea_gpu_assemble_all");
-        if (task->modified_newton) gpu_must(fea_gpu_restore_stiffness(solver->gpu), "fea_gpu_restore_stiffness");
+    /* The reference applies the whole increment at once (lambda = 1, :168).  If that inverts elements
+     * (det J <= 0 or det F <= 0 right after the boundary nodes moved: increments larger than an element)
+     * its log(J) turns NaN; here the increment is rolled back and applied in halves of what remains,
+     * each part equilibrated by the same Newton loop.  solver_update_nodes_with_bc and
+     * solver_apply_prescribed_bc already take the load fraction (fea_solver.c:573, :610). */
+    real remaining = 1.0, part = 1.0;
+    BOOL failed = FALSE;
+    while (remaining > 0.0 && !failed) {
+      int64_t bad = 0;
+      if (part > remaining) part = remaining;
+      gpu_must(fea_gpu_save_nodes(solver->gpu), "fea_gpu_save_nodes");
+      it = 0;
+      solver_update_nodes_with_bc(solver, part);                 /* full value every increment, :168 */
+      /* :171-179: gradients, stresses, K, keep K for modified Newton; the residual of the first
+       * iteration (:185) comes out of the same element pass */
+      gpu_must(fea_gpu_assemble_all(solver->gpu, 1), "fea_gpu_assemble_all");
+      gpu_must(fea_gpu_bad_points(solver->gpu, &bad), "fea_gpu_bad_points");
+      if (bad > 0 && part > 1.0 / 64.0) {
+        LOGERROR("Load increment %d: %ld Gauss points inverted by a load fraction of %g, halving it",
+                 solver->current_load_step + 1, (long)bad, part);
+        gpu_must(fea_gpu_restore_nodes(solver->gpu), "fea_gpu_restore_nodes");
+        part *= 0.5;
+        continue;
       }
-      solver_apply_prescribed_bc(solver, 0);                   /* :203 */
-      solver_solve_slae(solver);                               /* :205 */
-      gpu_must(fea_gpu_dot_R_u(solver->gpu, &tolerance), "fea_gpu_dot_R_u");   /* :208 */
-      LOG("Tolerance <X,R> = %e", tolerance);
-      LOG("Newton iteration %d finished", it);
-      solver_update_nodes_with_solution(solver, NULL);         /* :216 */
-    } while (fabs(tolerance) > task->desired_tolerance && it < task->max_newton_count);
+      gpu_must(fea_gpu_save_stiffness(solver->gpu), "fea_gpu_save_stiffness");
+      do {
+        real eta = 1.0;
+        it++;
+        if (it > 1) {
+          /* state of the updated nodes + residual (+ K for full Newton) in one pass */
+          gpu_must(fea_gpu_assemble_all(solver->gpu, task->modified_newton ? 0 : 1), "fea_gpu_assemble_all");
+          if (task->modified_newton) gpu_must(fea_gpu_restore_stiffness(solver->gpu), "fea_gpu_restore_stiffness");
+        }
+        solver_apply_prescribed_bc(solver, 0);                   /* :203 */
+        solver_solve_slae(solver);                               /* :205 */
+        gpu_must(fea_gpu_dot_R_u(solver->gpu, &tolerance), "fea_gpu_dot_R_u");   /* :208 */
+        LOG("Tolerance <X,R> = %e", tolerance);
+        if (task->linesearch_max > 0) {
+          gpu_must(fea_gpu_save_nodes(solver->gpu), "fea_gpu_save_nodes");
+          eta = solver_line_search(solver, tolerance, task->linesearch_max);
+          LOG("Line search: eta = %f", eta);
+        }
+        LOG("Newton iteration %d finished", it);
+        if (eta == 1.0)
+          solver_update_nodes_with_solution(solver, NULL);       /* :216 */
+        else
+          gpu_must(fea_gpu_update_nodes_scaled(solver->gpu, eta), "fea_gpu_update_nodes_scaled");
+      } while (fabs(tolerance) > task->desired_tolerance && it < task->max_newton_count);
+      if (it == task->max_newton_count) failed = TRUE;           /* the reference's test is on the count alone, :225 */
+      remaining -= part;
+      if (remaining > 0.0 && !failed)
+        LOG("Load increment %d: fraction %g done, %g to go", solver->current_load_step + 1, part, remaining);
+    }
     /* the reference recomputes gradients and stresses after the last update (:217-218) */
     solver_create_stresses(solver);
     LOG("Load increment %d finished", solver->current_load_step + 1);
-    if (it == task->max_newton_count) {                        /* :225-231 */
+    if (failed) {                                                /* :225-231 */
       solver->current_load_step--;
       LOGERROR("Unable to finish load step in %d Newton iterations,exit", task->max_newton_count);
       break;
     }
-    solver_load_step_init(solver, &solver->load_steps_p[solver->current_load_step], solver->current_load_step);
+    if (keep_steps || solver->current_load_step + 1 == task->load_increments_count)
+      solver_load_step_init(solver, &solver->load_steps_p[solver->current_load_step], solver->current_load_step);
   }
   LOG("Exporting data...");
   solver->export_function(solver, task->export_file);
@@ -491,6 +563,7 @@ void solver_export_tetrahedra10_gmsh(fea_solver_ptr solver, const char *filename
   fprintf(f, "$EndElements\n");
   for (load = 0; load <= solver->current_load_step; ++load) {
     const load_step *st = load ? &solver->load_steps_p[load - 1] : NULL;
+    if (st && !st->nodes_p) continue;                          /* FEA_KEEP_STEPS=0: increment not kept */
     fprintf(f, "$NodeData\n1\n\"Displacements\"\n1\n%f\n3\n%d\n3\n%d\n", load * 0.83333333, load, nn);
     for (i = 0; i < nn; ++i) {
       real u[3] = {0.0, 0.0, 0.0};

@@ -28,6 +28,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "fea_gpu_create", "fea_gpu_destroy", "fea_gpu_nccl_unique_id", "fea_gpu_last_error",
     "fea_gpu_set_nodes", "fea_gpu_get_nodes", "fea_gpu_apply_increment", "fea_gpu_update_nodes",
+    "fea_gpu_update_nodes_scaled", "fea_gpu_save_nodes", "fea_gpu_restore_nodes",
     "fea_gpu_update_state", "fea_gpu_assemble_stiffness", "fea_gpu_assemble_residual",
     "fea_gpu_assemble_all", "fea_gpu_apply_bc", "fea_gpu_save_stiffness", "fea_gpu_restore_stiffness",
     "fea_gpu_solve", "fea_gpu_dot_R_u", "fea_gpu_spmv", "fea_gpu_get_state", "fea_gpu_get_forces",
@@ -212,7 +213,8 @@ class FeaGpu:
         _check(f(C.byref(self.h), self.n_nodes, self.n_elems, nodes, conn, model, lam, mu, n_gauss, n_presc,
                  pn, pt, pv, rank, nranks, nccl_id, device))
         for name in ("update_state", "assemble_stiffness", "assemble_residual", "update_nodes",
-                     "save_stiffness", "restore_stiffness", "sync", "timer_start", "flush_l2"):
+                     "save_stiffness", "restore_stiffness", "sync", "timer_start", "flush_l2", "save_nodes",
+                     "restore_nodes"):
             getattr(L, "fea_gpu_" + name).argtypes = [C.c_void_p]
 
     def close(self):
@@ -235,6 +237,13 @@ class FeaGpu:
     def assemble_stiffness(self): self._simple("assemble_stiffness")
     def assemble_residual(self): self._simple("assemble_residual")
     def update_nodes(self): self._simple("update_nodes")
+    def save_nodes(self): self._simple("save_nodes")
+    def restore_nodes(self): self._simple("restore_nodes")
+
+    def update_nodes_scaled(self, eta):
+        lib().fea_gpu_update_nodes_scaled.argtypes = [C.c_void_p, C.c_double]
+        _check(lib().fea_gpu_update_nodes_scaled(self.h, float(eta)))
+
     def save_stiffness(self): self._simple("save_stiffness")
     def restore_stiffness(self): self._simple("restore_stiffness")
     def sync(self): self._simple("sync")
@@ -352,7 +361,7 @@ class FeaGpu:
         lib().fea_gpu_counts.argtypes = [C.c_void_p, _lp]
         _check(lib().fea_gpu_counts(self.h, out))
         keys = ["owned_nodes", "local_nodes", "local_elems", "nnzb", "contribs", "neighbours",
-                "halo_sent", "halo_recv", "global_nodes", "global_elems", "sell_slots", "sell_slices"]
+                "halo_sent", "halo_recv", "global_nodes", "global_elems", "sell_slots", "sell_slices", "gather9"]
         return dict(zip(keys, (int(v) for v in out)))
 
     def phase_ms(self):

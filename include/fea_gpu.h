@@ -90,6 +90,13 @@ int fea_gpu_get_nodes(fea_gpu_handle h, double *x);
 int fea_gpu_apply_increment(fea_gpu_handle h, double lambda);
 /* solver_update_nodes_with_solution(self, global_solution_vct) (:1270-1279) */
 int fea_gpu_update_nodes(fea_gpu_handle h);
+/* nodes_p += eta * global_solution_vct: the step of a line search along the Newton direction
+ * (solver-prototype/cartesian3d/large/cartesian3d_large.m:85-119 evaluates R at nodes1 + eta X) */
+int fea_gpu_update_nodes_scaled(fea_gpu_handle h, double eta);
+/* keep / restore nodes_p on the device: the `nodes1 = nodes` of the prototype's line search (:65) and the
+ * roll-back of a load increment that inverted elements (host/fea_solver.c: solve) */
+int fea_gpu_save_nodes(fea_gpu_handle h);
+int fea_gpu_restore_nodes(fea_gpu_handle h);
 
 /* ---- element phase ----------------------------------------------------- */
 
@@ -178,7 +185,8 @@ int fea_gpu_step_from_host(fea_gpu_handle h, const double *x, int32_t with_stiff
 /* out[0]=owned nodes, [1]=local nodes (owned+ghost), [2]=local elements,
  * [3]=block nonzeros (3x3), [4]=gather contributions, [5]=neighbour ranks,
  * [6]=halo nodes sent, [7]=halo nodes received, [8]=global nodes, [9]=global elements,
- * [10]=SELL block slots (incl. padding), [11]=SELL slices */
+ * [10]=SELL block slots (incl. padding), [11]=SELL slices, [12]=1 if the nine-lane gather can run
+ * on this pattern (fea_gpu_counts only) */
 int fea_gpu_counts(fea_gpu_handle h, int64_t out[16]);
 /* kernels launched by this library in this process (all handles) */
 int64_t fea_gpu_launch_count(void);

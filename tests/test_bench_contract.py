@@ -96,7 +96,7 @@ def test_own_arm_line_small_workload():
                   "--cpu-newton-sample", "3", "--c4-n", "8", "--parity-sample", "4")
     p = d["parity"]
     assert p["ok"] and p["max_rel_elem"] <= 1e-11 and p["bench_mesh_window"]["K_e_compared_all_ranks"] > 0
-    assert d["strong_c4"]["pcg_exit"] == 1 and d["strong_c4"]["elements"] == 6 * 8 ** 3 and d["comm"]["halo_ms"] == 0.0
+    assert d["strong_c4"]["pcg_exit"] == 1 and d["strong_c4"]["elements"] == 6 * 8 ** 3 and d["comm"]["halo_ms"] < 1e-3
     assert d["cpu_baseline"]["newton"]["pcg_iters"] > 0 and d["roofline_fp64"]["dmma_m8n8k4_tflops_this_run"] > 0
     assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak"

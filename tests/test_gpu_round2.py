@@ -27,6 +27,7 @@ def test_gather_modes_agree_bitwise(case):
     vals = {}
     for mode in (1, 9):
         g = make_gpu(m)
+        assert g.counts()["gather9"] == 1                      # the nine-lane kernel is what mode 9 runs here
         g.set_param("gather_mode", mode)
         g.set_nodes(x)
         g.assemble_all(True)
