@@ -12,7 +12,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -66,7 +70,10 @@ constexpr int PHASE_EVENT_POOL = 32;
 constexpr int MAX_PARTIALS = 4096;
 constexpr size_t FLUSH_BYTES = 512ull << 20;
 
+struct fea_gpu_group;
+
 struct fea_gpu_ctx {
+  fea_gpu_group *group = nullptr;   // set when this context is one rank of a single-process multi-GPU handle
   fea::Plan plan;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -141,7 +148,82 @@ struct fea_gpu_ctx {
   cudaEvent_t tm_a = nullptr, tm_b = nullptr;
   std::vector<int32_t> own_count;  // owned nodes per rank
   std::vector<int32_t> elem_g2l;   // lazily built: global element id -> local element (-1 = not on this rank)
+  double *ag_send = nullptr, *ag_recv = nullptr;   // all-gather buffers of the read-backs (allocated once)
+  double *ag_host = nullptr;                       // pinned
 };
+
+// ---------------------------------------------------------------------------------
+// Single-process multi-GPU handle (fea_gpu_create_multi): one context per GPU, one persistent host thread
+// per context.  Every C-ABI call on the handle runs on all ranks at once -- the calls are the same
+// rank-local calls a one-process-per-GPU launcher makes, NCCL included -- so the reference's one-process
+// boundary (do_main -> solve, fea_solver.c:100-242) can drive the whole box.
+
+struct fea_gpu_group {
+  std::vector<fea_gpu_ctx *> ctx;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::function<int(int)> job;
+  uint64_t generation = 0;
+  int pending = 0;
+  bool stop = false;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+};
+
+static thread_local bool t_worker = false;   // true on the group's rank threads: calls go straight to the context
+
+static void group_worker(fea_gpu_group *G, int i) {
+  t_worker = true;
+  uint64_t seen = 0;
+  for (;;) {
+    std::function<int(int)> job;
+    {
+      std::unique_lock<std::mutex> lk(G->mu);
+      G->cv_job.wait(lk, [&] { return G->stop || G->generation != seen; });
+      if (G->stop) return;
+      seen = G->generation;
+      job = G->job;
+    }
+    const int rc = job(i);
+    {
+      std::lock_guard<std::mutex> lk(G->mu);
+      G->rc[(size_t)i] = rc;
+      G->err[(size_t)i] = rc != FEA_GPU_OK ? g_err : std::string();
+      if (--G->pending == 0) G->cv_done.notify_all();
+    }
+  }
+}
+
+// run f(rank) on every rank thread, wait for all; first non-zero return code wins
+static int group_run(fea_gpu_group *G, std::function<int(int)> f) {
+  std::unique_lock<std::mutex> lk(G->mu);
+  G->job = std::move(f);
+  G->pending = (int)G->threads.size();
+  ++G->generation;
+  G->cv_job.notify_all();
+  G->cv_done.wait(lk, [&] { return G->pending == 0; });
+  for (size_t i = 0; i < G->rc.size(); ++i)
+    if (G->rc[i] != FEA_GPU_OK) {
+      g_err = "rank " + std::to_string(i) + ": " + G->err[i];
+      return G->rc[i];
+    }
+  return FEA_GPU_OK;
+}
+
+// first statement of every entry point that takes a handle: on a multi-GPU handle run `expr` (written in
+// terms of the rank's context `ci` and its rank `gi`) on all rank threads
+#define GROUP(c, ...)                                                                    \
+  do {                                                                                   \
+    if ((c) && (c)->group && !t_worker) {                                                \
+      fea_gpu_group *G_ = (c)->group;                                                    \
+      return group_run(G_, [&](int gi) -> int {                                          \
+        fea_gpu_ctx *ci = G_->ctx[(size_t)gi];                                           \
+        (void)ci;                                                                        \
+        return __VA_ARGS__;                                                              \
+      });                                                                                \
+    }                                                                                    \
+  } while (0)
 
 template <class T>
 static int dev_alloc(T **p, size_t n) {
@@ -537,8 +619,64 @@ extern "C" int fea_gpu_create(fea_gpu_handle *out, int32_t n_nodes, int32_t n_el
   return FEA_GPU_OK;
 }
 
+static void group_stop(fea_gpu_group *G) {
+  {
+    std::lock_guard<std::mutex> lk(G->mu);
+    G->stop = true;
+  }
+  G->cv_job.notify_all();
+  for (std::thread &t : G->threads) t.join();
+  delete G;
+}
+
+// One process, n_gpus GPUs: the same arguments as fea_gpu_create without the rank plumbing.  The handle
+// that comes back stands for all ranks; every other entry point accepts it.
+extern "C" int fea_gpu_create_multi(fea_gpu_handle *out, int32_t n_nodes, int32_t n_elems, const double *X0,
+                                    const int32_t *conn, int32_t model_type, double lambda, double mu,
+                                    int32_t n_gauss, int32_t n_presc, const int32_t *presc_node,
+                                    const int32_t *presc_type, const double *presc_vals, int32_t n_gpus,
+                                    const int32_t *devices) {
+  if (!out || n_gpus < 1) return FEA_GPU_ERR_ARG;
+  if (n_gpus == 1)
+    return fea_gpu_create(out, n_nodes, n_elems, X0, conn, model_type, lambda, mu, n_gauss, n_presc, presc_node,
+                          presc_type, presc_vals, 0, 1, nullptr, devices ? devices[0] : 0);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev < n_gpus) {
+    g_err = "fea_gpu_create_multi: " + std::to_string(n_gpus) + " GPUs asked, " + std::to_string(ndev) + " visible";
+    return FEA_GPU_ERR_CUDA;
+  }
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  fea_gpu_group *G = new fea_gpu_group();
+  G->ctx.assign((size_t)n_gpus, nullptr);
+  G->rc.assign((size_t)n_gpus, 0);
+  G->err.assign((size_t)n_gpus, std::string());
+  for (int i = 0; i < n_gpus; ++i) G->threads.emplace_back(group_worker, G, i);
+  const int rc = group_run(G, [&](int gi) -> int {
+    return fea_gpu_create(&G->ctx[(size_t)gi], n_nodes, n_elems, X0, conn, model_type, lambda, mu, n_gauss, n_presc,
+                          presc_node, presc_type, presc_vals, gi, n_gpus, &id, devices ? devices[gi] : gi);
+  });
+  if (rc != FEA_GPU_OK) {
+    const std::string why = g_err;
+    group_run(G, [&](int gi) -> int { return G->ctx[(size_t)gi] ? fea_gpu_destroy(G->ctx[(size_t)gi]) : FEA_GPU_OK; });
+    group_stop(G);
+    g_err = why;
+    return rc;
+  }
+  for (fea_gpu_ctx *ci : G->ctx) ci->group = G;
+  *out = G->ctx[0];
+  return FEA_GPU_OK;
+}
+
 extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (!c) return FEA_GPU_OK;
+  if (c->group && !t_worker) {
+    fea_gpu_group *G = c->group;
+    group_run(G, [&](int gi) -> int { return fea_gpu_destroy(G->ctx[(size_t)gi]); });
+    group_stop(G);
+    return FEA_GPU_OK;
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->has_comm) ncclCommDestroy(c->comm);
@@ -546,11 +684,12 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
-                  c->flush, c->export_buf, c->x_saved, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
+                  c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
   if (c->st2_host) cudaFreeHost(c->st2_host);
+  if (c->ag_host) cudaFreeHost(c->ag_host);
   if (c->ev_vec) cudaEventDestroy(c->ev_vec);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -586,9 +725,11 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
 // ---------------------------------------------------------------------------------
 // vectors between the caller's global numbering and the rank-local device layout
 
+// host_global == nullptr: take part in the collective, place nothing (ranks > 0 of a multi-GPU handle)
 static int gather_owned(fea_gpu_ctx *c, const double *dev_vec, double *host_global) {
   const fea::Plan &pl = c->plan;
   if (!c->has_comm) {
+    if (!host_global) return FEA_GPU_OK;
     std::vector<double> tmp(3 * (size_t)c->n_own);
     CU(cudaMemcpyAsync(tmp.data(), dev_vec, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -596,29 +737,27 @@ static int gather_owned(fea_gpu_ctx *c, const double *dev_vec, double *host_glob
       std::memcpy(host_global + 3 * (size_t)pl.node_gid[(size_t)l], tmp.data() + 3 * (size_t)l, 3 * sizeof(double));
     return FEA_GPU_OK;
   }
-  // all-gather of equally padded owned blocks, then placement by the shared owner map
+  // all-gather of equally padded owned blocks, then placement by the shared owner map.  The buffers are
+  // allocated once: cudaMalloc / cudaFree around a collective would serialise the ranks of a one-process box
   int32_t maxown = 0;
   for (int32_t v : c->own_count) maxown = std::max(maxown, v);
   const size_t blk = 3 * (size_t)maxown;
-  double *sbuf = nullptr, *rbuf = nullptr;
-  std::vector<double> tmp(blk * (size_t)pl.nranks);
-  auto body = [&]() -> int {
-    TRY(dev_alloc(&sbuf, blk));
-    TRY(dev_alloc(&rbuf, blk * (size_t)pl.nranks));
-    CU(cudaMemsetAsync(sbuf, 0, sizeof(double) * blk, c->stream));
-    CU(cudaMemcpyAsync(sbuf, dev_vec, sizeof(double) * 3 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
-    NC(ncclAllGather(sbuf, rbuf, blk, ncclDouble, c->comm, c->stream));
-    CU(cudaMemcpyAsync(tmp.data(), rbuf, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return FEA_GPU_OK;
-  };
-  const int rc = body();
-  cudaFree(sbuf);
-  cudaFree(rbuf);
-  if (rc != FEA_GPU_OK) return rc;
+  if (!c->ag_send) {
+    TRY(dev_alloc(&c->ag_send, blk));
+    TRY(dev_alloc(&c->ag_recv, blk * (size_t)pl.nranks));
+    CU(cudaHostAlloc((void **)&c->ag_host, sizeof(double) * blk * (size_t)pl.nranks, cudaHostAllocDefault));
+  }
+  CU(cudaMemsetAsync(c->ag_send, 0, sizeof(double) * blk, c->stream));
+  CU(cudaMemcpyAsync(c->ag_send, dev_vec, sizeof(double) * 3 * (size_t)c->n_own, cudaMemcpyDeviceToDevice, c->stream));
+  NC(ncclAllGather(c->ag_send, c->ag_recv, blk, ncclDouble, c->comm, c->stream));
+  if (host_global)
+    CU(cudaMemcpyAsync(c->ag_host, c->ag_recv, sizeof(double) * blk * (size_t)pl.nranks, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (!host_global) return FEA_GPU_OK;
+#pragma omp parallel for schedule(static)
   for (int64_t g = 0; g < pl.n_nodes_global; ++g) {  // every rank knows every owner's numbering
     const int o = pl.owner[(size_t)g];
-    std::memcpy(host_global + 3 * (size_t)g, tmp.data() + blk * (size_t)o + 3 * (size_t)pl.pos_in_owner[(size_t)g],
+    std::memcpy(host_global + 3 * (size_t)g, c->ag_host + blk * (size_t)o + 3 * (size_t)pl.pos_in_owner[(size_t)g],
                 3 * sizeof(double));
   }
   return FEA_GPU_OK;
@@ -635,32 +774,38 @@ static int scatter_local(fea_gpu_ctx *c, const double *host_global, double *dev_
 }
 
 extern "C" int fea_gpu_set_nodes(fea_gpu_handle c, const double *x) {
+  GROUP(c, fea_gpu_set_nodes(ci, x));
   CHECK_H(c);
   if (!x) return FEA_GPU_ERR_ARG;
   return scatter_local(c, x, c->x, c->n_local);
 }
 extern "C" int fea_gpu_get_nodes(fea_gpu_handle c, double *x) {
+  GROUP(c, fea_gpu_get_nodes(ci, gi ? nullptr : x));
   CHECK_H(c);
-  if (!x) return FEA_GPU_ERR_ARG;
+  if (!x && !(c->group && t_worker)) return FEA_GPU_ERR_ARG;
   return gather_owned(c, c->x, x);
 }
 extern "C" int fea_gpu_get_forces(fea_gpu_handle c, double *R) {
+  GROUP(c, fea_gpu_get_forces(ci, gi ? nullptr : R));
   CHECK_H(c);
-  if (!R) return FEA_GPU_ERR_ARG;
+  if (!R && !(c->group && t_worker)) return FEA_GPU_ERR_ARG;
   return gather_owned(c, c->R, R);
 }
 extern "C" int fea_gpu_set_forces(fea_gpu_handle c, const double *R) {
+  GROUP(c, fea_gpu_set_forces(ci, R));
   CHECK_H(c);
   if (!R) return FEA_GPU_ERR_ARG;
   return scatter_local(c, R, c->R, c->n_own);
 }
 extern "C" int fea_gpu_get_solution(fea_gpu_handle c, double *u) {
+  GROUP(c, fea_gpu_get_solution(ci, gi ? nullptr : u));
   CHECK_H(c);
-  if (!u) return FEA_GPU_ERR_ARG;
+  if (!u && !(c->group && t_worker)) return FEA_GPU_ERR_ARG;
   return gather_owned(c, c->u, u);
 }
 
 extern "C" int fea_gpu_apply_increment(fea_gpu_handle c, double lambda) {
+  GROUP(c, fea_gpu_apply_increment(ci, lambda));
   CHECK_H(c);
   if (c->n_inc) {
     fea::increment_kernel<<<cdiv(c->n_inc, 256), 256, 0, c->stream>>>(c->n_inc, c->inc_dof, c->inc_val, lambda, c->x);
@@ -670,6 +815,7 @@ extern "C" int fea_gpu_apply_increment(fea_gpu_handle c, double lambda) {
 }
 
 extern "C" int fea_gpu_update_nodes_scaled(fea_gpu_handle c, double eta) {
+  GROUP(c, fea_gpu_update_nodes_scaled(ci, eta));
   CHECK_H(c);
   const int n = 3 * c->n_own;
   fea::axpy_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, eta, c->u, c->x);
@@ -682,6 +828,7 @@ extern "C" int fea_gpu_update_nodes_scaled(fea_gpu_handle c, double eta) {
 extern "C" int fea_gpu_update_nodes(fea_gpu_handle c) { return fea_gpu_update_nodes_scaled(c, 1.0); }
 
 extern "C" int fea_gpu_save_nodes(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_save_nodes(ci));
   CHECK_H(c);
   const size_t nl3 = 3 * (size_t)c->n_local;
   if (!c->x_saved) TRY(dev_alloc(&c->x_saved, nl3));
@@ -689,6 +836,7 @@ extern "C" int fea_gpu_save_nodes(fea_gpu_handle c) {
   return FEA_GPU_OK;
 }
 extern "C" int fea_gpu_restore_nodes(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_restore_nodes(ci));
   CHECK_H(c);
   if (!c->x_saved) {
     g_err = "no saved nodes";
@@ -791,20 +939,24 @@ static int gather_residual(fea_gpu_ctx *c) {
 }
 
 extern "C" int fea_gpu_update_state(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_update_state(ci));
   CHECK_H(c);
   return element_pass(c, false, false);
 }
 extern "C" int fea_gpu_assemble_stiffness(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_assemble_stiffness(ci));
   CHECK_H(c);
   TRY(element_pass(c, true, false));
   return gather_stiffness(c, false);
 }
 extern "C" int fea_gpu_assemble_residual(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_assemble_residual(ci));
   CHECK_H(c);
   TRY(element_pass(c, false, true));
   return gather_residual(c);
 }
 extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t flags) {
+  GROUP(c, fea_gpu_assemble_all(ci, flags));
   CHECK_H(c);
   const bool with_k = (flags & FEA_ASSEMBLE_STIFFNESS) != 0, fuse_bc = (flags & FEA_ASSEMBLE_FUSE_BC) != 0;
   TRY(element_pass(c, with_k, true));
@@ -821,6 +973,14 @@ extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t flags) {
 }
 
 extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
+  if (c && c->group && !t_worker) {   // sum over the ranks (interface elements are seen by every rank that computes them)
+    if (!count) return FEA_GPU_ERR_ARG;
+    std::vector<int64_t> part(c->group->ctx.size(), 0);
+    const int rc = group_run(c->group, [&](int gi) { return fea_gpu_bad_points(c->group->ctx[(size_t)gi], &part[(size_t)gi]); });
+    *count = 0;
+    for (int64_t v : part) *count += v;
+    return rc;
+  }
   CHECK_H(c);
   if (!count) return FEA_GPU_ERR_ARG;
   unsigned long long v = 0;
@@ -857,6 +1017,7 @@ static int launch_spmv(fea_gpu_ctx *c, const double *x, double *y, bool fuse_dot
 }
 
 extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
+  GROUP(c, fea_gpu_apply_bc(ci, lambda));
   CHECK_H(c);
   phase_begin(c, PH_BC);
   const int n = 3 * c->n_own;
@@ -879,12 +1040,14 @@ extern "C" int fea_gpu_apply_bc(fea_gpu_handle c, double lambda) {
 }
 
 extern "C" int fea_gpu_save_stiffness(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_save_stiffness(ci));
   CHECK_H(c);
   if (!c->vals_saved) TRY(dev_alloc(&c->vals_saved, (size_t)c->n_slots * 9));
   CU(cudaMemcpyAsync(c->vals_saved, c->vals, sizeof(double) * (size_t)c->n_slots * 9, cudaMemcpyDeviceToDevice, c->stream));
   return FEA_GPU_OK;
 }
 extern "C" int fea_gpu_restore_stiffness(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_restore_stiffness(ci));
   CHECK_H(c);
   if (!c->vals_saved) {
     g_err = "no saved stiffness";
@@ -1058,6 +1221,16 @@ static int solve_single_reduction(fea_gpu_ctx *c, double tol, int32_t max_iter, 
 
 extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int32_t flags, int32_t *iters,
                              double *relres) {
+  if (c && c->group && !t_worker) {   // every rank returns the same (all-reduced) record
+    std::vector<int32_t> it(c->group->ctx.size(), 0);
+    std::vector<double> rr(c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) {
+      return fea_gpu_solve(c->group->ctx[(size_t)gi], tol, max_iter, flags, &it[(size_t)gi], &rr[(size_t)gi]);
+    });
+    if (iters) *iters = it[0];
+    if (relres) *relres = rr[0];
+    return rc;
+  }
   CHECK_H(c);
   if (max_iter < 0 || !(tol >= 0.0)) return FEA_GPU_ERR_ARG;
   const int n = 3 * c->n_own;
@@ -1094,6 +1267,13 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
 }
 
 extern "C" int fea_gpu_dot_R_u(fea_gpu_handle c, double *out) {
+  if (c && c->group && !t_worker) {
+    if (!out) return FEA_GPU_ERR_ARG;
+    std::vector<double> v(c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) { return fea_gpu_dot_R_u(c->group->ctx[(size_t)gi], &v[(size_t)gi]); });
+    *out = v[0];
+    return rc;
+  }
   CHECK_H(c);
   if (!out) return FEA_GPU_ERR_ARG;
   const int n = 3 * c->n_own;
@@ -1107,14 +1287,21 @@ extern "C" int fea_gpu_dot_R_u(fea_gpu_handle c, double *out) {
 }
 
 extern "C" int fea_gpu_spmv(fea_gpu_handle c, const double *x, double *y) {
+  GROUP(c, fea_gpu_spmv(ci, x, gi ? nullptr : y));
   CHECK_H(c);
-  if (!x || !y) return FEA_GPU_ERR_ARG;
+  if (!x || (!y && !(c->group && t_worker))) return FEA_GPU_ERR_ARG;
   TRY(scatter_local(c, x, c->p, c->n_local));
   TRY(launch_spmv(c, c->p, c->q, false));
   return gather_owned(c, c->q, y);
 }
 
 extern "C" int fea_gpu_bench_spmv(fea_gpu_handle c, int32_t reps, double *ms_per_spmv) {
+  if (c && c->group && !t_worker) {
+    std::vector<double> v(c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) { return fea_gpu_bench_spmv(c->group->ctx[(size_t)gi], reps, &v[(size_t)gi]); });
+    if (ms_per_spmv) *ms_per_spmv = *std::max_element(v.begin(), v.end());
+    return rc;
+  }
   CHECK_H(c);
   if (reps < 1 || !ms_per_spmv) return FEA_GPU_ERR_ARG;
   TRY(launch_spmv(c, c->p, c->q, false));  // warm
@@ -1132,6 +1319,7 @@ extern "C" int fea_gpu_bench_spmv(fea_gpu_handle c, int32_t reps, double *ms_per
 // read-back
 
 extern "C" int fea_gpu_get_state(fea_gpu_handle c, double *graddefs, double *stresses) {
+  GROUP(c, fea_gpu_get_state(ci, graddefs, stresses));
   CHECK_H(c);
   const fea::Plan &pl = c->plan;
   const size_t per = (size_t)c->ng * 9;
@@ -1164,6 +1352,19 @@ static void ensure_elem_map(fea_gpu_ctx *c) {
 // rank (owned or an interface element it computes redundantly), else its output rows are left untouched.
 extern "C" int fea_gpu_get_state_elems(fea_gpu_handle c, int32_t n, const int32_t *elems, double *graddefs,
                                        double *stresses, int32_t *found) {
+  if (c && c->group && !t_worker) {   // rank by rank: a later rank overwrites identical values, masks are OR-ed
+    std::vector<int32_t> f((size_t)std::max(n, 0), 0);
+    if (found) std::fill(found, found + std::max(n, 0), 0);
+    for (fea_gpu_ctx *ci : c->group->ctx) {
+      t_worker = true;
+      const int rc = fea_gpu_get_state_elems(ci, n, elems, graddefs, stresses, f.data());
+      t_worker = false;
+      if (rc != FEA_GPU_OK) return rc;
+      if (found)
+        for (int32_t k = 0; k < n; ++k) found[k] |= f[(size_t)k];
+    }
+    return FEA_GPU_OK;
+  }
   CHECK_H(c);
   if (n < 0 || (n > 0 && !elems)) return FEA_GPU_ERR_ARG;
   if (n == 0) return FEA_GPU_OK;
@@ -1206,6 +1407,16 @@ extern "C" int fea_gpu_get_state_elems(fea_gpu_handle c, int32_t n, const int32_
 // [3a+i][3b+j] the reference builds in solver_local_constitutive_part + solver_local_initial_stess_part
 // (fea_solver.c:887-1068; compare with the capture at its sp_matrix_element_add call sites).
 extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, double *ke900) {
+  if (c && c->group && !t_worker) {
+    int rc = FEA_GPU_ERR_ARG;
+    for (fea_gpu_ctx *ci : c->group->ctx) {
+      t_worker = true;
+      rc = fea_gpu_get_element_matrix(ci, element, ke900);
+      t_worker = false;
+      if (rc != FEA_GPU_ERR_ARG) break;
+    }
+    return rc;
+  }
   CHECK_H(c);
   if (!ke900 || element < 0 || element >= c->plan.n_elems_global) return FEA_GPU_ERR_ARG;
   if (FEA_KE_INTERLEAVED) {
@@ -1236,6 +1447,10 @@ extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, dou
 
 extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, int32_t *rows, int32_t *rowptr,
                                int32_t *colidx, double *vals) {
+  if (c && c->group && !t_worker) {
+    g_err = "fea_gpu_get_csr returns the rows of ONE rank: not available on a multi-GPU handle";
+    return FEA_GPU_ERR_ARG;
+  }
   CHECK_H(c);
   const fea::Plan &pl = c->plan;
   // a node that belongs to no element carries an internal lone diagonal block (so Jacobi has a
@@ -1300,6 +1515,15 @@ extern "C" int fea_gpu_host_free(void *p) {
 
 extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t with_stiffness, double *R,
                                       uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+  if (c && c->group && !t_worker) {   // every rank fills its own rows of R
+    std::vector<uint64_t> a(c->group->ctx.size(), 0), b(c->group->ctx.size(), 0);
+    const int rc = group_run(c->group, [&](int gi) {
+      return fea_gpu_step_from_host(c->group->ctx[(size_t)gi], x, with_stiffness, R, &a[(size_t)gi], &b[(size_t)gi]);
+    });
+    if (h2d_bytes) { *h2d_bytes = 0; for (uint64_t v : a) *h2d_bytes += v; }
+    if (d2h_bytes) { *d2h_bytes = 0; for (uint64_t v : b) *d2h_bytes += v; }
+    return rc;
+  }
   CHECK_H(c);
   if (!x || !R) return FEA_GPU_ERR_ARG;
   const fea::Plan &pl = c->plan;
@@ -1355,22 +1579,45 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
 
 extern "C" int fea_gpu_counts(fea_gpu_handle c, int64_t out[16]) {
   if (!c || !out) return FEA_GPU_ERR_ARG;
+  if (c->group && !t_worker) {        // sums over the ranks where a sum means something, else the maximum
+    int64_t tmp[16];
+    std::memset(out, 0, sizeof(int64_t) * 16);
+    for (fea_gpu_ctx *ci : c->group->ctx) {
+      fea::plan_counts(ci->plan, tmp);
+      tmp[12] = ci->gather9_ok ? 1 : 0;
+      for (int k : {0, 3, 4, 6, 7, 10, 11}) out[k] += tmp[k];
+      for (int k : {1, 2, 5}) out[k] = std::max(out[k], tmp[k]);
+      out[8] = tmp[8];
+      out[9] = tmp[9];
+      out[12] = ci == c->group->ctx[0] ? tmp[12] : std::min(out[12], tmp[12]);
+    }
+    out[13] = (int64_t)c->group->ctx.size();
+    return FEA_GPU_OK;
+  }
   fea::plan_counts(c->plan, out);
   out[12] = c->gather9_ok ? 1 : 0;
   return FEA_GPU_OK;
 }
 
 extern "C" int fea_gpu_sync(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_sync(ci));
   CHECK_H(c);
   CU(cudaStreamSynchronize(c->stream));
   return FEA_GPU_OK;
 }
 extern "C" int fea_gpu_timer_start(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_timer_start(ci));
   CHECK_H(c);
   CU(cudaEventRecord(c->tm_a, c->stream));
   return FEA_GPU_OK;
 }
 extern "C" int fea_gpu_timer_stop(fea_gpu_handle c, double *ms) {
+  if (c && c->group && !t_worker) {
+    std::vector<double> v(c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) { return fea_gpu_timer_stop(c->group->ctx[(size_t)gi], &v[(size_t)gi]); });
+    if (ms) *ms = *std::max_element(v.begin(), v.end());
+    return rc;
+  }
   CHECK_H(c);
   CU(cudaEventRecord(c->tm_b, c->stream));
   CU(cudaEventSynchronize(c->tm_b));
@@ -1381,6 +1628,17 @@ extern "C" int fea_gpu_timer_stop(fea_gpu_handle c, double *ms) {
 }
 
 extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
+  if (c && c->group && !t_worker) {
+    if (!out) return FEA_GPU_ERR_ARG;
+    std::vector<double> v(16 * c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) { return fea_gpu_phase_ms(c->group->ctx[(size_t)gi], &v[16 * (size_t)gi]); });
+    for (int k = 0; k < 16; ++k) {
+      out[k] = v[(size_t)k];
+      if (k < 8)
+        for (size_t r = 1; r < c->group->ctx.size(); ++r) out[k] = std::max(out[k], v[16 * r + (size_t)k]);
+    }
+    return rc;
+  }
   CHECK_H(c);
   if (!out) return FEA_GPU_ERR_ARG;
   CU(cudaStreamSynchronize(c->stream));
@@ -1421,6 +1679,15 @@ extern "C" int fea_gpu_phase_ms(fea_gpu_handle c, double out[16]) {
 
 extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double value) {
   if (!c || !name) return FEA_GPU_ERR_ARG;
+  if (c->group && !t_worker) {
+    for (fea_gpu_ctx *ci : c->group->ctx) {
+      t_worker = true;
+      const int rc = fea_gpu_set_param(ci, name, value);
+      t_worker = false;
+      if (rc != FEA_GPU_OK) return rc;
+    }
+    return FEA_GPU_OK;
+  }
   const std::string k(name);
   const int v = (int)value;
   if (k == "gather_threads" && (v == 128 || v == 256 || v == 512 || v == 1024)) c->gather_threads = v;
@@ -1472,6 +1739,15 @@ extern "C" int fea_gpu_measure_dmma(int32_t device, double *dmma_tflops) {
 // average device time of the two collectives of a PCG iteration, each timed alone on the context's
 // stream: the halo exchange of a [n_local][3] vector and the all-reduce of the four iteration sums
 extern "C" int fea_gpu_bench_comm(fea_gpu_handle c, int32_t reps, double *halo_ms, double *allreduce_ms) {
+  if (c && c->group && !t_worker) {
+    std::vector<double> a(c->group->ctx.size(), 0.0), b(c->group->ctx.size(), 0.0);
+    const int rc = group_run(c->group, [&](int gi) {
+      return fea_gpu_bench_comm(c->group->ctx[(size_t)gi], reps, &a[(size_t)gi], &b[(size_t)gi]);
+    });
+    if (halo_ms) *halo_ms = *std::max_element(a.begin(), a.end());
+    if (allreduce_ms) *allreduce_ms = *std::max_element(b.begin(), b.end());
+    return rc;
+  }
   CHECK_H(c);
   if (reps < 1) return FEA_GPU_ERR_ARG;
   float ms = 0;
@@ -1498,6 +1774,7 @@ extern "C" int fea_gpu_bench_comm(fea_gpu_handle c, int32_t reps, double *halo_m
 }
 
 extern "C" int fea_gpu_flush_l2(fea_gpu_handle c) {
+  GROUP(c, fea_gpu_flush_l2(ci));
   CHECK_H(c);
   if (!c->flush) CU(cudaMalloc(&c->flush, FLUSH_BYTES));
   CU(cudaMemsetAsync(c->flush, 1, FLUSH_BYTES, c->stream));

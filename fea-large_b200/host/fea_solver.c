@@ -366,7 +366,8 @@ fea_solver_ptr fea_solver_alloc(fea_task_ptr task, fea_solution_params_ptr fea_p
   const int elnum = elements->elements_count, ng = fea_params->gauss_nodes_count, np = presc->prescribed_nodes_count;
   int *pnode = (int *)malloc(sizeof(int) * (size_t)(np + 1)), *ptype = (int *)malloc(sizeof(int) * (size_t)(np + 1));
   real *pval = (real *)malloc(sizeof(real) * 3 * (size_t)(np + 1));
-  const char *dev = getenv("FEA_GPU_DEVICE");
+  const char *dev = getenv("FEA_GPU_DEVICE"), *cnt = getenv("FEA_GPU_COUNT");
+  const int n_gpus = cnt && atoi(cnt) > 1 ? atoi(cnt) : 1;   /* FEA_GPU_COUNT=8: this process drives the whole box */
   int i, d, rc;
   s->task_p = task;
   s->fea_params_p = fea_params;
@@ -389,10 +390,16 @@ fea_solver_ptr fea_solver_alloc(fea_task_ptr task, fea_solution_params_ptr fea_p
     ptype[i] = (int)presc->prescribed_nodes[i].type;
     for (d = 0; d < 3; ++d) pval[3 * i + d] = presc->prescribed_nodes[i].values[d];
   }
-  rc = fea_gpu_create(&s->gpu, nodes->nodes_count, elnum, nodes->nodes[0], elements->elements[0],
-                      task->model.model == MODEL_A5 ? FEA_MODEL_A5 : FEA_MODEL_COMPRESSIBLE_NEOHOOKEAN,
-                      task->model.parameters[0], task->model.parameters[1], ng, np, pnode, ptype, pval,
-                      0, 1, NULL, dev ? atoi(dev) : 0);
+  if (n_gpus > 1)
+    rc = fea_gpu_create_multi(&s->gpu, nodes->nodes_count, elnum, nodes->nodes[0], elements->elements[0],
+                              task->model.model == MODEL_A5 ? FEA_MODEL_A5 : FEA_MODEL_COMPRESSIBLE_NEOHOOKEAN,
+                              task->model.parameters[0], task->model.parameters[1], ng, np, pnode, ptype, pval,
+                              n_gpus, NULL);
+  else
+    rc = fea_gpu_create(&s->gpu, nodes->nodes_count, elnum, nodes->nodes[0], elements->elements[0],
+                        task->model.model == MODEL_A5 ? FEA_MODEL_A5 : FEA_MODEL_COMPRESSIBLE_NEOHOOKEAN,
+                        task->model.parameters[0], task->model.parameters[1], ng, np, pnode, ptype, pval,
+                        0, 1, NULL, dev ? atoi(dev) : 0);
   free(pnode);
   free(ptype);
   free(pval);

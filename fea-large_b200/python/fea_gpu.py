@@ -26,7 +26,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 # every symbol include/fea_gpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "fea_gpu_create", "fea_gpu_destroy", "fea_gpu_nccl_unique_id", "fea_gpu_last_error",
+    "fea_gpu_create", "fea_gpu_create_multi", "fea_gpu_destroy", "fea_gpu_nccl_unique_id", "fea_gpu_last_error",
     "fea_gpu_set_nodes", "fea_gpu_get_nodes", "fea_gpu_apply_increment", "fea_gpu_update_nodes",
     "fea_gpu_update_nodes_scaled", "fea_gpu_save_nodes", "fea_gpu_restore_nodes",
     "fea_gpu_update_state", "fea_gpu_assemble_stiffness", "fea_gpu_assemble_residual",
@@ -196,7 +196,7 @@ class FeaGpu:
     """One GPU context (= one rank).  Methods mirror the C-ABI one to one."""
 
     def __init__(self, nodes, conn, model, lam, mu, n_gauss=5, presc_node=None, presc_type=None,
-                 presc_vals=None, rank=0, nranks=1, nccl_id=None, device=0):
+                 presc_vals=None, rank=0, nranks=1, nccl_id=None, device=0, n_gpus=None):
         L = lib()
         nodes = np.ascontiguousarray(nodes, np.float64)
         conn = np.ascontiguousarray(conn, np.int32)
@@ -207,11 +207,18 @@ class FeaGpu:
         self.n_nodes, self.n_elems, self.ng = len(nodes), len(conn), n_gauss
         self.n = 3 * self.n_nodes
         self.h = C.c_void_p()
-        f = L.fea_gpu_create
-        f.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp, _ip, C.c_int32, C.c_double, C.c_double,
-                      C.c_int32, C.c_int32, _ip, _ip, _dp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
-        _check(f(C.byref(self.h), self.n_nodes, self.n_elems, nodes, conn, model, lam, mu, n_gauss, n_presc,
-                 pn, pt, pv, rank, nranks, nccl_id, device))
+        if n_gpus is not None:      # one process, several GPUs (fea_gpu_create_multi)
+            f = L.fea_gpu_create_multi
+            f.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp, _ip, C.c_int32, C.c_double, C.c_double,
+                          C.c_int32, C.c_int32, _ip, _ip, _dp, C.c_int32, C.c_void_p]
+            _check(f(C.byref(self.h), self.n_nodes, self.n_elems, nodes, conn, model, lam, mu, n_gauss, n_presc,
+                     pn, pt, pv, int(n_gpus), None))
+        else:
+            f = L.fea_gpu_create
+            f.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp, _ip, C.c_int32, C.c_double, C.c_double,
+                          C.c_int32, C.c_int32, _ip, _ip, _dp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+            _check(f(C.byref(self.h), self.n_nodes, self.n_elems, nodes, conn, model, lam, mu, n_gauss, n_presc,
+                     pn, pt, pv, rank, nranks, nccl_id, device))
         for name in ("update_state", "assemble_stiffness", "assemble_residual", "update_nodes",
                      "save_stiffness", "restore_stiffness", "sync", "timer_start", "flush_l2", "save_nodes",
                      "restore_nodes"):

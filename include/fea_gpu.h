@@ -74,6 +74,19 @@ int fea_gpu_create(fea_gpu_handle *out, int32_t n_nodes, int32_t n_elems,
                    const int32_t *presc_node, const int32_t *presc_type,
                    const double *presc_vals, int32_t rank, int32_t nranks,
                    const void *nccl_unique_id, int32_t device);
+/*
+ * The same for ONE process driving n_gpus GPUs of the box (the reference's boundary is one process:
+ * do_main -> solve, fea_solver.c:100-242).  The library creates one context and one host thread per GPU
+ * (devices[i], or 0..n_gpus-1 when devices is NULL) and its own NCCL communicator; the handle that comes
+ * back stands for all ranks and every entry point below accepts it: phase calls run on all ranks at
+ * once, read-backs return the assembled global arrays, scalar results are the all-reduced ones.
+ * fea_gpu_get_csr is per rank and not available on such a handle.  fea_gpu_counts [13] = ranks.
+ */
+int fea_gpu_create_multi(fea_gpu_handle *out, int32_t n_nodes, int32_t n_elems,
+                         const double *X0, const int32_t *conn, int32_t model_type,
+                         double lambda, double mu, int32_t n_gauss, int32_t n_presc,
+                         const int32_t *presc_node, const int32_t *presc_type,
+                         const double *presc_vals, int32_t n_gpus, const int32_t *devices);
 /* fea_solver_free (fea_solver.c:459-501) */
 int fea_gpu_destroy(fea_gpu_handle h);
 /* ncclGetUniqueId for the caller to broadcast (128 bytes) */

@@ -92,7 +92,7 @@ def write_sexp(path, m, load_increments=2, shuffle_keys=False):
                     f":max-newton-count {m.max_newton}\n")
         f.write(f"   (element-type :gauss-nodes-count {m.gauss} :name TETRAHEDRA10 :nodes-count 10)\n")
         f.write(f"   (slae-solver :type {solver} :tolerance {float(m.solver_tolerance)!r} :max-iterations {m.solver_max_iter})\n")
-        f.write("   (line-search :max 0)\n   (arc-length :max 0))\n (input-data\n  (geometry\n   (nodes\n")
+        f.write(f"   (line-search :max {int(m.extra.get('linesearch', 0))})\n   (arc-length :max 0))\n (input-data\n  (geometry\n   (nodes\n")
         for x in m.nodes:
             f.write(f"    ({float(x[0])!r} {float(x[1])!r} {float(x[2])!r})\n")
         f.write("   )\n   (elements\n")

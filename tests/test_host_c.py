@@ -182,3 +182,76 @@ def test_feasolver_reports_nonconvergence_like_the_reference(host, tmp_path):
     # current_load_step is rolled back to -1, so the reference's export loop (load <= step,
     # :1440) writes the mesh and no data sections at all
     assert msh.count("$Nodes") == 1 and msh.count("$NodeData") == 0
+
+
+def _msh_sections(path):
+    """{(kind, step): array} of the $NodeData / $ElementData blocks of a Gmsh 2.0 file."""
+    out, lines, i = {}, open(path).read().splitlines(), 0
+    while i < len(lines):
+        if lines[i] in ("$NodeData", "$ElementData"):
+            kind, step, n = lines[i], int(lines[i + 6]), int(lines[i + 8])
+            out[(kind, step)] = np.array([_numbers(l)[1:] for l in lines[i + 9:i + 9 + n]])
+            i += 9 + n
+        else:
+            i += 1
+    return out
+
+
+@pytest.mark.gpu
+def test_feasolver_halves_an_increment_that_inverts_elements(host, tmp_path):
+    """One increment of 1.2 element heights on a uniaxial bar: the boundary move alone folds the top layer
+    (mid-side nodes end up beyond the quarter point), where the reference's log(det F) turns NaN
+    (fea_model.c:105).  solve() rolls the increment back and applies it in halves; the converged state is
+    the homogeneous one of exact-solutions/uniaxial at the full stretch."""
+    from oracle.oracle import uniaxial_neohookean
+    m = block_model((2, 2, 2), model=1, bc_style=2, dy=0.6)
+    m.desired_tolerance, m.max_newton, m.solver_type, m.modified_newton = 1e-14, 60, 0, False
+    path = str(tmp_path / "fold.sexp")
+    write_sexp(path, m, load_increments=1)
+    run = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert "Gauss points inverted by a load fraction of 1, halving it" in run.stdout
+    assert "Load increment 1 finished" in run.stdout and "Unable to finish" not in run.stdout
+    sec = _msh_sections(str(tmp_path / "fold.msh"))
+    u, sig = sec[("$NodeData", 1)], sec[("$ElementData", 1)]
+    k2, syy = uniaxial_neohookean(1.6)
+    assert abs(u[:, 1].max() - 0.6) < 2e-6                       # the whole increment was applied
+    assert np.abs(sig[:, 4] - syy).max() < 1e-4 * syy            # %f carries six decimals
+    assert np.abs(sig[:, [0, 8]]).max() < 1e-4                   # lateral faces stress free
+
+
+@pytest.mark.gpu
+def test_feasolver_line_search_as_the_prototype(host, tmp_path):
+    """:line-search :max 3 -- golden-section probes of |eta <u, R(x + eta u)>| on [0.5, 1]
+    (solver-prototype/cartesian3d/large/cartesian3d_large.m:85-119); with :max 0 solve() is the shipped one.
+    Both runs must land on the same equilibrium."""
+    outs = {}
+    for ls in (0, 3):
+        m, _ = load_golden("neohook_brick")
+        m.desired_tolerance, m.max_newton, m.modified_newton = 1e-12, 60, False
+        m.extra["linesearch"] = ls
+        path = str(tmp_path / f"ls{ls}.sexp")
+        write_sexp(path, m, load_increments=1)
+        run = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+        assert run.returncode == 0, run.stderr[-2000:]
+        assert ("Line search: eta" in run.stdout) == (ls > 0)
+        assert "Unable to finish" not in run.stdout
+        outs[ls] = _msh_sections(str(tmp_path / f"ls{ls}.msh"))[("$NodeData", 1)]
+    assert np.abs(outs[0] - outs[3]).max() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_feasolver_without_per_increment_snapshots(host, tmp_path):
+    """FEA_KEEP_STEPS=0: only the last increment is pulled to the host and exported (fea_solver.c:605-636 keeps all)."""
+    m, _ = load_golden("a5_brick")
+    path = str(tmp_path / "keep.sexp")
+    write_sexp(path, m, load_increments=2)
+    full = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    a = _msh_sections(str(tmp_path / "keep.msh"))
+    last = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600,
+                          env=dict(os.environ, FEA_KEEP_STEPS="0"))
+    b = _msh_sections(str(tmp_path / "keep.msh"))
+    assert full.returncode == 0 and last.returncode == 0
+    assert set(a) == {(k, s) for k in ("$NodeData", "$ElementData") for s in (0, 1, 2)}
+    assert set(b) == {(k, s) for k in ("$NodeData", "$ElementData") for s in (0, 2)}
+    assert np.array_equal(a[("$NodeData", 2)], b[("$NodeData", 2)])
