@@ -647,7 +647,8 @@ def strong_c4(args, fg, rank, world, local_rank, new_nccl_id, barrier, allmax, a
     cnt = g.counts()
     setup_s = allmax(time.time() - t0)
     g.apply_increment(1.0)
-    g.assemble_all(True, fuse_bc=True)      # warm
+    g.update_nodes()                        # warm, the halo exchange included (NCCL sets its peer channels up on first use)
+    g.assemble_all(True, fuse_bc=True)
     g.sync()
     g.phase_ms()
     barrier()

@@ -41,7 +41,10 @@ constexpr int ELEMS_PER_CTA = 32;
 // t_a = (mu' wd I + s) g_a itself (9 FMAs + 3 adds per Gauss point and row) instead of reading it.
 constexpr int FLD_DOUBLES = 38 * 32;          // doubles per Gauss point
 constexpr int FLD_SG = 10 * 64, FLD_LM = 13 * 64, FLD_G2 = 14 * 64;
-constexpr int TILE_D2 = 9 * 32;               // double2 per warp: the store-transpose tile of one block pair
+#ifndef FEA_KE_TMA_STORE
+#define FEA_KE_TMA_STORE 0
+#endif
+constexpr int TILE_D2 = (FEA_KE_TMA_STORE ? 2 : 1) * 9 * 32;   // double2 per warp: the store tile of one block pair (two with the bulk-copy engine)
 
 struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
@@ -292,6 +295,9 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
     for (int it = 0; it < 9; ++it)
       if ((it * 32 + lane) / 9 < n_here) vmask |= 1u << it;
     double *kcta = A.Ke + (size_t)e0 * KE_STRIDE;
+#if FEA_KE_TMA_STORE
+    int tma_flip = 0;
+#endif
     for (int pr = gp; pr < 5; pr += NG)
       for (int half = 0; half < 2; ++half) {
         const int a = half ? 9 - pr : pr;
@@ -394,6 +400,37 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           continue;
 #endif
           double *dst = kcta + 100 * pr + 9 * ke_pos(a, b);
+#if FEA_KE_TMA_STORE
+          // Bulk-copy engine variant: every thread parks its 144 (80) bytes in its own row of the warp's
+          // tile and hands them to the TMA unit with one cp.async.bulk (shared -> global); no LDS / STG
+          // through the LSU pipe at all.  Two tile rows per thread alternate, so the wait for the engine to
+          // have READ a row comes one block pair late.
+          {
+            double2 *t = tile + ((tma_flip & 1) * 32 + lane) * 9;
+            if (tma_flip >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            t[0] = make_double2(k0[0], k0[1]);
+            t[1] = make_double2(k0[2], k0[3]);
+            t[2] = make_double2(k0[4], k0[5]);
+            t[3] = make_double2(k0[6], k0[7]);
+            t[4] = make_double2(k0[8], two ? k1[0] : 0.0);
+            if (two) {
+              t[5] = make_double2(k1[1], k1[2]);
+              t[6] = make_double2(k1[3], k1[4]);
+              t[7] = make_double2(k1[5], k1[6]);
+              t[8] = make_double2(k1[7], k1[8]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (live) {
+              const unsigned src = (unsigned)__cvta_generic_to_shared(t);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + lane * KE_STRIDE),
+                           "r"(src), "r"(two ? 144 : 80)
+                           : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++tma_flip;
+          }
+          continue;
+#endif
           if (two) {
             double2 *t = tile + lane * 9;
             t[0] = make_double2(k0[0], k0[1]);
@@ -432,6 +469,9 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         }
       }
   }
+#if FEA_KE_TMA_STORE
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine must have read the tile before the CTA retires
+#endif
 #undef GA2
 #undef SG2
 #undef LM2

@@ -96,7 +96,7 @@ struct fea_gpu_ctx {
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
-  int gather_mode = 9;             // 9 = nine lanes per block (gather_blocks9_kernel), 1 = lane per slot (gather_blocks_kernel)
+  int gather_mode = 1;             // 1 = lane per slot (gather_blocks_kernel, default), 9 = nine lanes per block (gather_blocks9_kernel: 41 % fewer L1 sectors, same time -- DESIGN 4)
   bool gather9_ok = false;         // the uploaded lists satisfy what gather_blocks9_kernel assumes
 
   double *X0 = nullptr, *x = nullptr;
@@ -123,6 +123,7 @@ struct fea_gpu_ctx {
   int32_t *send_nodes = nullptr;
   double *send_buf = nullptr;
   double *partials = nullptr;
+  double *partials_b = nullptr;    // grid-reduction scratch of the boundary SpMV (it runs beside the interior one)
   unsigned int *counters = nullptr;
   PcgCtl *ctl = nullptr;
   PcgCtl *ctl_host = nullptr;
@@ -354,6 +355,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   if (const char *s = getenv("FEA_GATHER_THREADS")) fea_gpu_set_param(c, "gather_threads", atof(s));
   if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
   if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
+  if (const char *s = getenv("FEA_PCG_VARIANT")) fea_gpu_set_param(c, "pcg_variant", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
     int v = atoi(s);
     if (v >= 1 && v <= 4096) c->pcg_batch = v;
@@ -538,6 +540,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   TRY(dev_alloc(&c->dinv, n3));
   TRY(dev_alloc(&c->u_saved, n3));
   TRY(dev_alloc(&c->partials, 3 * (size_t)MAX_PARTIALS));
+  TRY(dev_alloc(&c->partials_b, (size_t)MAX_PARTIALS));
   TRY(dev_alloc(&c->counters, 8));
   TRY(dev_alloc(&c->ctl, 1));
   TRY(dev_alloc(&c->scalar, 4));
@@ -683,7 +686,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   void *ptrs[] = {c->X0, c->x, c->conn_soa, c->F_soa, c->S_soa, c->Ke, c->Re, c->slice_ptr, c->sell_row, c->bcol,
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
-                  c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->counters, c->ctl, c->scalar, c->bad,
+                  c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->partials_b, c->counters, c->ctl, c->scalar, c->bad,
                   c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -915,7 +918,7 @@ static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
     if (c->gather_mode == 9 && c->gather9_ok && !FEA_KE_INTERLEAVED)
-      fea::gather_blocks9_kernel<4, 10><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
+      fea::gather_blocks9_kernel<4, FEA_G9_MINCTAS><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
     else
     switch (c->gather_threads) {
       case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
@@ -996,18 +999,21 @@ extern "C" int fea_gpu_bad_points(fea_gpu_handle c, int64_t *count) {
 // y = K x over all slices, or over the slices of `list`; with `dot_out` the partial of x . y of those rows
 // is reduced (fixed order) into *dot_out and the launch is a no-op once *done_flag is set
 static int launch_spmv_list(fea_gpu_ctx *c, const double *x, double *y, double *dot_out, const int *done_flag,
-                            const int32_t *list, int n_list) {
+                            const int32_t *list, int n_list, bool side = false) {
+  cudaStream_t st = side ? c->comm_stream : c->stream;          // side: the boundary slices, beside the interior ones
+  double *scratch = side ? c->partials_b : c->partials;
+  unsigned int *counter = c->counters + (side ? 4 : 0);
   if (n_list <= 0) {
-    if (dot_out) CU(cudaMemsetAsync(dot_out, 0, sizeof(double), c->stream));
+    if (dot_out) CU(cudaMemsetAsync(dot_out, 0, sizeof(double), st));
     return FEA_GPU_OK;
   }
   const int grid = std::min(cdiv((int64_t)n_list * 32, 256), MAX_PARTIALS);
   if (dot_out)
-    fea::spmv_sell_kernel<true><<<grid, 256, 0, c->stream>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y,
-                                                             c->partials, c->counters + 0, dot_out, done_flag, list);
+    fea::spmv_sell_kernel<true><<<grid, 256, 0, st>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y, scratch,
+                                                      counter, dot_out, done_flag, list);
   else
-    fea::spmv_sell_kernel<false><<<grid, 256, 0, c->stream>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y,
-                                                              c->partials, c->counters + 0, nullptr, nullptr, list);
+    fea::spmv_sell_kernel<false><<<grid, 256, 0, st>>>(n_list, c->slice_ptr, c->sell_row, c->bcol, c->vals, x, y, scratch,
+                                                       counter, nullptr, nullptr, list);
   LAUNCHED();
   return FEA_GPU_OK;
 }
@@ -1076,15 +1082,17 @@ static int spmv_with_halo(fea_gpu_ctx *c, double *z, double *w, double *dot_a, d
     if (dot_b) CU(cudaMemsetAsync(dot_b, 0, sizeof(double), c->stream));
     return FEA_GPU_OK;
   }
+  // comm stream: pack, send / receive, then the few slices that need the ghost values; main stream: all the
+  // others meanwhile.  The two products write disjoint rows of w and reduce their dot partials separately.
   CU(cudaEventRecord(c->ev_vec, c->stream));
   CU(cudaStreamWaitEvent(c->comm_stream, c->ev_vec, 0));
   TRY(halo_exchange(c, z, c->comm_stream));
+  TRY(launch_spmv_list(c, z, w, dot_b, done_flag, c->sl_bound, c->n_bound, true));
   CU(cudaEventRecord(c->ev_halo, c->comm_stream));
   if (timed) cudaEventRecord(c->sp_a[c->sp_used], c->stream);
   TRY(launch_spmv_list(c, z, w, dot_a, done_flag, c->sl_inner, c->n_inner));
+  if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);   // the interior product (the boundary one runs beside it)
   CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  TRY(launch_spmv_list(c, z, w, dot_b, done_flag, c->sl_bound, c->n_bound));
-  if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);   // both parts (and any wait for the halo)
   return FEA_GPU_OK;
 }
 

@@ -202,6 +202,12 @@ gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, con
 // otherwise.  A slot's sum runs in list order in one register, exactly as in gather_item (same bits).
 // The Dirichlet flags are applied where the column leaves the tile for the SELL value array (lane = slot
 // again: nine coalesced 256-byte stores).
+#ifndef FEA_G9_NOPRED
+#define FEA_G9_NOPRED 1
+#endif
+#ifndef FEA_G9_MINCTAS
+#define FEA_G9_MINCTAS 10
+#endif
 constexpr int GATHER9_UNROLL = 8;
 constexpr uint32_t SRC_LAST = 0x40000000u;     // device copy of csrc only: last entry of its slot
 constexpr uint32_t SRC_IDX_MASK = 0x3fffffffu;
@@ -248,8 +254,14 @@ gather_blocks9_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, co
       for (int u = 0; u < GATHER9_UNROLL; ++u) {
         const uint32_t idx = src[u] & SRC_IDX_MASK;        // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp)
         const size_t off = (size_t)idx * 9 + idx / 11u;
+#if FEA_G9_NOPRED
+        // beyond its range a group's list word is 0: block 0 of element 0, a harmless (cached) load whose
+        // value is added after the group's last mark and never stored
+        v[u] = ((src[u] >> 31) ? KeT : KeC)[off];
+#else
         v[u] = 0.0;
         if (t + u < te) v[u] = ((src[u] >> 31) ? KeT : KeC)[off];
+#endif
       }
 #pragma unroll
       for (int u = 0; u < GATHER9_UNROLL; ++u) {
