@@ -544,7 +544,7 @@ def main():
                   "pcg_tol": args.lin_tol, "pcg_exit": exits, "pcg_exit_legend": "1 = tolerance met, 2 = stall/divergence guard, 0 = max_iter",
                   "pcg_iters_per_sec": float(sum(its) / (sum(nt_ms) * 1e-3)),
                   "pcg_ms_per_iter": float(sum(pcg_ms) / max(sum(its), 1)),
-                  "pcg_variant": "single reduction (Chronopoulos-Gear), halo beside the interior slices" if world > 1 else "classic",
+                  "pcg_variant": "single reduction (Chronopoulos-Gear), one all-reduce of 4 doubles per iteration" if world > 1 else "classic",
                   "spmv_ms": sp, "spmv_format": "3x3 blocks in SELL-32-sigma, fp64 values, int32 block columns",
                   "nnz_scalar_total": 9 * nnzb}
     comm = {"halo_ms": allmax(halo_ms), "allreduce_ms": allmax(allreduce_ms), "halo_x_ms_in_step": allmax(halo_x_ms),

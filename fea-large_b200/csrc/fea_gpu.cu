@@ -91,7 +91,7 @@ struct fea_gpu_ctx {
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
   int pcg_variant = -1;            // 0 = classic PCG (two reductions), 1 = single reduction, -1 = 1 iff nranks > 1
-  int pcg_overlap = 1;             // halo exchange on its own stream beside the interior SpMV slices
+  int pcg_overlap = 0;             // 1 = halo exchange + boundary slices on a second stream beside the interior SpMV (measured slower at N = 2: 0.748 vs 0.684 ms per iteration, the cross-stream events cost more than the 19 us halo they hide)
   int last_exit = 0;               // exit state of the last solve: 0 max_iter, 1 tolerance, 2 stall/divergence guard
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
@@ -356,6 +356,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
   if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
   if (const char *s = getenv("FEA_PCG_VARIANT")) fea_gpu_set_param(c, "pcg_variant", atof(s));
+  if (const char *s = getenv("FEA_PCG_OVERLAP")) fea_gpu_set_param(c, "pcg_overlap", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
     int v = atoi(s);
     if (v >= 1 && v <= 4096) c->pcg_batch = v;
