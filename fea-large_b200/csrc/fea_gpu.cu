@@ -90,9 +90,17 @@ struct fea_gpu_ctx {
   int64_t n_slots = 0;
   int pcg_batch = 32;
   int pcg_stall = 0;               // 0 = automatic
-  int pcg_variant = -1;            // 0 = classic PCG (two reductions), 1 = single reduction, -1 = 1 iff nranks > 1
+  int pcg_variant = 0;             // 0 = classic PCG (two reductions per iteration, default), 1 = single reduction
+                                   // (Chronopoulos-Gear: measured 1 % faster at N = 2 and NOT robust -- its alpha
+                                   // denominator cancels when ||r|| peaks: breakdown at iteration 220 on a 16 k-DOF bar
+                                   // that classic PCG solves in 1039, reproduced in numpy)
   int pcg_overlap = 0;             // 1 = halo exchange + boundary slices on a second stream beside the interior SpMV (measured slower at N = 2: 0.748 vs 0.684 ms per iteration, the cross-stream events cost more than the 19 us halo they hide)
   int last_exit = 0;               // exit state of the last solve: 0 max_iter, 1 tolerance, 2 stall/divergence guard
+  int precond = 0;                 // 0 = Jacobi (north star), 1 = Chebyshev-accelerated Jacobi (the PCG_ILU request)
+  int cheb_degree = 4;
+  double cheb_ratio = 100.0;       // the polynomial targets [lmax / ratio, lmax] of D^-1 A
+  double last_lmax = 0.0;
+  double *cz = nullptr, *cd = nullptr;   // Chebyshev iterate z ([n_local][3]: it is an SpMV input) and increment d
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
@@ -688,7 +696,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->partials_b, c->counters, c->ctl, c->scalar, c->bad,
-                  c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
+                  c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->cz, c->cd, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -1228,6 +1236,125 @@ static int solve_single_reduction(fea_gpu_ctx *c, double tol, int32_t max_iter, 
   return FEA_GPU_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Chebyshev-Jacobi PCG (the PCG_ILU request of a task file): classic recurrences, general preconditioner
+
+static int dot_to(fea_gpu_ctx *c, const double *a, const double *b, double *dev_out) {
+  const int n = 3 * c->n_own;
+  fea::dot_kernel<<<std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS), fea::RED_THREADS, 0, c->stream>>>(
+      n, a, b, c->partials, c->counters + 3, dev_out);
+  LAUNCHED();
+  return allreduce_sum(c, dev_out, 1);
+}
+
+// upper bound of the spectrum of D^-1 A: power iteration (it converges from below; the safety factor and the
+// fact that the top of an FE spectrum is dense make 1.2 x the estimate an upper bound in practice)
+static int estimate_lmax(fea_gpu_ctx *c, double *lmax) {
+  const int n = 3 * c->n_own, grid = std::min(cdiv(n, 256), 148 * 8);
+  fea::power_start_kernel<<<grid, 256, 0, c->stream>>>(n, c->cz);
+  LAUNCHED();
+  TRY(dot_to(c, c->cz, c->cz, c->scalar));
+  for (int it = 0; it < 30; ++it) {
+    TRY(halo_exchange(c, c->cz));
+    TRY(launch_spmv(c, c->cz, c->q, false));
+    fea::scale_dinv_kernel<<<grid, 256, 0, c->stream>>>(n, c->q, c->dinv, c->scalar, c->cz);   // D^-1 A v / |v|
+    LAUNCHED();
+    TRY(dot_to(c, c->cz, c->cz, c->scalar));
+  }
+  double nrm2 = 0;
+  CU(cudaMemcpyAsync(&nrm2, c->scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  // after the last step cz = D^-1 A v_prev / |v_prev| with v_prev the previous (unnormalised) iterate: |cz| -> lmax
+  *lmax = std::sqrt(nrm2);
+  return FEA_GPU_OK;
+}
+
+// z = p_d(D^-1 A) D^-1 r  (z in c->cz)
+static int chebyshev_apply(fea_gpu_ctx *c, const double *r, double lmax) {
+  const int n = 3 * c->n_own, grid = std::min(cdiv(n, 256), 148 * 8);
+  const double b = lmax, a = lmax / c->cheb_ratio, theta = 0.5 * (b + a), delta = 0.5 * (b - a), sigma = theta / delta;
+  fea::cheb_first_kernel<<<grid, 256, 0, c->stream>>>(n, r, c->dinv, 1.0 / theta, c->cd, c->cz);
+  LAUNCHED();
+  double rho = 1.0 / sigma;
+  for (int k = 1; k < c->cheb_degree; ++k) {
+    const double rho2 = 1.0 / (2.0 * sigma - rho);
+    TRY(halo_exchange(c, c->cz));
+    TRY(launch_spmv(c, c->cz, c->q, false));
+    fea::cheb_step_kernel<<<grid, 256, 0, c->stream>>>(n, r, c->q, c->dinv, rho2 * rho, 2.0 * rho2 / delta, c->cd, c->cz);
+    LAUNCHED();
+    rho = rho2;
+  }
+  return FEA_GPU_OK;
+}
+
+static int solve_chebyshev(fea_gpu_ctx *c, double tol, int32_t max_iter, int32_t flags, SolveExit *ex) {
+  const int n = 3 * c->n_own;
+  const int abs_tol = (flags & FEA_SOLVE_ABS_TOL) ? 1 : 0;
+  const int vgrid = std::min(cdiv(n, fea::RED_THREADS), MAX_PARTIALS / 4);
+  if (!c->cz) TRY(dev_alloc(&c->cz, 3 * (size_t)c->n_local));
+  if (!c->cd) TRY(dev_alloc(&c->cd, (size_t)n));
+  CU(cudaMemsetAsync(c->cz, 0, sizeof(double) * 3 * (size_t)c->n_local, c->stream));
+  double lmax = 0;
+  TRY(estimate_lmax(c, &lmax));
+  lmax *= 1.2;
+  c->last_lmax = lmax;
+  const int stall_limit = stall_limit_of(c);
+  CU(cudaMemcpyAsync(&c->ctl->stall_limit, &stall_limit, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const double *q0 = nullptr;
+  if (flags & FEA_SOLVE_X0_RHS) {
+    CU(cudaMemcpyAsync(c->u, c->R, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    TRY(halo_exchange(c, c->u));
+    TRY(launch_spmv(c, c->u, c->q, false));
+    q0 = c->q;
+  } else {
+    CU(cudaMemsetAsync(c->u, 0, sizeof(double) * (size_t)n, c->stream));
+  }
+  // r, b.b, r.r from the Jacobi start kernel (finalize = 0: the sums are completed below); then z, p = z, r.z
+  fea::pcg_init_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->R, q0, c->dinv, c->r, c->p, c->partials,
+                                                                  c->counters + 1, c->ctl, tol, abs_tol, 0);
+  LAUNCHED();
+  TRY(allreduce_sum(c, &c->ctl->rz_new, 3));    // (rz_new, rr, bb) are contiguous; rz_new is replaced next
+  TRY(chebyshev_apply(c, c->r, lmax));
+  CU(cudaMemcpyAsync(c->p, c->cz, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+  TRY(dot_to(c, c->r, c->cz, &c->ctl->rz_new));
+  fea::pcg_init_finalize_kernel<<<1, 1, 0, c->stream>>>(c->ctl, tol, abs_tol);
+  LAUNCHED();
+  CU(cudaMemcpyAsync(c->u_saved, c->u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+  int launched = 0;
+  bool done = false;
+  const int batch_cap = std::max(1, c->pcg_batch / c->cheb_degree);
+  while (!done) {
+    const int batch = std::min(batch_cap, max_iter - launched);
+    for (int bi = 0; bi < batch; ++bi) {
+      TRY(halo_exchange(c, c->p));
+      const bool timed = c->sp_used < SPMV_EVENT_POOL;
+      if (timed) cudaEventRecord(c->sp_a[c->sp_used], c->stream);
+      TRY(launch_spmv(c, c->p, c->q, true));
+      if (timed) cudaEventRecord(c->sp_b[c->sp_used++], c->stream);
+      TRY(allreduce_sum(c, &c->ctl->pq, 1));
+      fea::pcg_update_kernel<<<vgrid, fea::RED_THREADS, 0, c->stream>>>(n, c->p, c->q, c->dinv, c->u, c->r, c->partials,
+                                                                        c->counters + 2, c->ctl, 0);
+      LAUNCHED();
+      TRY(allreduce_sum(c, &c->ctl->rr, 1));
+      TRY(chebyshev_apply(c, c->r, lmax));      // (a few wasted products after convergence inside a batch)
+      TRY(dot_to(c, c->r, c->cz, &c->ctl->rz_new));
+      fea::pcg_control_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
+      LAUNCHED();
+      fea::pcg_direction_z_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, c->cz, c->p, c->u, c->u_saved, c->ctl);
+      LAUNCHED();
+    }
+    launched += batch;
+    CU(cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    done = c->ctl_host->done || launched >= max_iter;
+  }
+  ex->done = c->ctl_host->done;
+  ex->iters = c->ctl_host->iters;
+  ex->bb = c->ctl_host->bb;
+  ex->rr_final = c->ctl_host->done == 2 ? c->ctl_host->rr_saved : c->ctl_host->rr_exit;
+  return FEA_GPU_OK;
+}
+
 extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int32_t flags, int32_t *iters,
                              double *relres) {
   if (c && c->group && !t_worker) {   // every rank returns the same (all-reduced) record
@@ -1248,8 +1375,10 @@ extern "C" int fea_gpu_solve(fea_gpu_handle c, double tol, int32_t max_iter, int
   fea::jacobi_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vals, c->sdiag, c->dinv);
   LAUNCHED();
   SolveExit ex;
-  const bool single_reduction = c->pcg_variant < 0 ? c->has_comm : c->pcg_variant == 1;
-  if (single_reduction)
+  const bool single_reduction = c->pcg_variant == 1;
+  if (c->precond == 1)
+    TRY(solve_chebyshev(c, tol, max_iter, flags, &ex));
+  else if (single_reduction)
     TRY(solve_single_reduction(c, tol, max_iter, flags, &ex));
   else
     TRY(solve_classic(c, tol, max_iter, flags, &ex));
@@ -1705,7 +1834,10 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   else if (k == "gather_mode" && (v == 1 || v == 9)) c->gather_mode = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
-  else if (k == "pcg_variant" && v >= -1 && v <= 1) c->pcg_variant = v;
+  else if (k == "pcg_variant" && v >= 0 && v <= 1) c->pcg_variant = v;
+  else if (k == "precond" && (v == 0 || v == 1)) c->precond = v;
+  else if (k == "cheb_degree" && v >= 1 && v <= 16) c->cheb_degree = v;
+  else if (k == "cheb_ratio" && value >= 2.0 && value <= 1e4) c->cheb_ratio = value;
   else if (k == "pcg_overlap" && (v == 0 || v == 1)) c->pcg_overlap = v;
   else {
     g_err = "unknown parameter or value out of range: " + k;

@@ -689,6 +689,56 @@ pcg2_step_kernel(int n, const Pcg2State *__restrict__ Sc, Pcg2State *Sn, double 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Chebyshev-accelerated Jacobi: the stronger preconditioner behind the task files' PCG_ILU request
+// (fea_solver.c:260-280 builds an incomplete factorisation there; triangular solves do not map onto
+// 148 SMs, a fixed polynomial in D^-1 A does -- it is a fixed SPD operator, so CG stays CG).
+//   z = p_d(D^-1 A) D^-1 r: d steps of the Chebyshev iteration for A z = r on [lmax / ratio, lmax]
+//     d_0 = D^-1 r / theta, z = d_0;   d_k = rho_k rho_{k-1} d_{k-1} + (2 rho_k / delta) D^-1 (r - A z),  z += d_k
+
+__global__ void cheb_first_kernel(int n, const double *__restrict__ r, const double *__restrict__ dinv,
+                                  double inv_theta, double *__restrict__ d, double *__restrict__ z) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double v = dinv[t] * r[t] * inv_theta;
+    d[t] = v;
+    z[t] = v;
+  }
+}
+
+__global__ void cheb_step_kernel(int n, const double *__restrict__ r, const double *__restrict__ w /* A z */,
+                                 const double *__restrict__ dinv, double c1, double c2, double *__restrict__ d,
+                                 double *__restrict__ z) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double v = fma(c1, d[t], c2 * (dinv[t] * (r[t] - w[t])));
+    d[t] = v;
+    z[t] += v;
+  }
+}
+
+// p = z + beta p (general preconditioner); when the control block asks for it, checkpoint u
+__global__ void __launch_bounds__(256)
+pcg_direction_z_kernel(int n, const double *__restrict__ z, double *__restrict__ p, const double *__restrict__ u,
+                       double *__restrict__ u_saved, const PcgCtl *ctl) {
+  if (ctl->done) return;
+  const double beta = ctl->beta;
+  const bool save = ctl->save != 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    p[t] = fma(beta, p[t], z[t]);
+    if (save) u_saved[t] = u[t];
+  }
+}
+
+// v <- D^-1 w / sqrt(*nrm2_prev) ... pieces of the power iteration that bounds the spectrum of D^-1 A
+__global__ void scale_dinv_kernel(int n, const double *__restrict__ w, const double *__restrict__ dinv,
+                                  const double *__restrict__ nrm2 /* null: no scaling */, double *__restrict__ v) {
+  const double s = nrm2 ? rsqrt(*nrm2) : 1.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) v[t] = dinv[t] * w[t] * s;
+}
+__global__ void power_start_kernel(int n, double *__restrict__ v) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    v[t] = 1.0 + 0.25 * (double)((t * 2654435761u) >> 29);   // fixed, not orthogonal to anything in particular
+}
+
 // out = a . b (fixed order)
 __global__ void __launch_bounds__(RED_THREADS)
 dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b, double *partials,

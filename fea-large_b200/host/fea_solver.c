@@ -470,6 +470,9 @@ BOOL solver_solve_slae(fea_solver_ptr solver) {
   int32_t iters = 0;
   int rc;
   LOGINFO("Starting to solve SLAE");
+  /* PCG_ILU (fea_solver.c:260-280) asks for a stronger preconditioner than plain CG: Chebyshev-accelerated
+   * Jacobi on the device; CG and CHOLESKY run the north star's Jacobi-PCG */
+  gpu_must(fea_gpu_set_param(solver->gpu, "precond", t->solver_type == PCG_ILU ? 1 : 0), "fea_gpu_set_param");
   rc = fea_gpu_solve(solver->gpu, tol, max_iter, FEA_SOLVE_X0_ZERO, &iters, &solver->last_linear_residual);
   solver->last_linear_iterations = iters;
   if (rc == FEA_GPU_ERR_STALLED)      /* u holds the best checkpointed iterate; the Newton loop goes on with it */

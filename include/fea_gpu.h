@@ -144,9 +144,9 @@ int fea_gpu_restore_stiffness(fea_gpu_handle h);
  * near-minimum-residual iterate in u and returns FEA_GPU_ERR_STALLED (FEA_GPU_OK under
  * FEA_SOLVE_ACCEPT_STALL); `relres` tells what was reached.  iters/relres may be NULL.
  * Returns FEA_GPU_ERR_NOT_CONVERGED at max_iter.
- * With nranks > 1 the single-reduction (Chronopoulos-Gear) form of the same iteration runs: one
- * all-reduce of four doubles per iteration ("pcg_variant" in fea_gpu_set_param; "pcg_overlap" = 1 also
- * moves the halo exchange and the rows that need ghost values to a second stream). */
+ * "pcg_variant" = 1 (fea_gpu_set_param) runs the single-reduction (Chronopoulos-Gear) form of the same
+ * iteration -- one all-reduce of four doubles per iteration instead of two small ones; it is not the
+ * default because its step-length recurrence can break down where classic PCG converges. */
 int fea_gpu_solve(fea_gpu_handle h, double tol, int32_t max_iter, int32_t flags,
                   int32_t *iters, double *relres);
 /* cdot(global_forces_vct, global_solution_vct, n) at :208 */
@@ -227,8 +227,12 @@ int fea_gpu_measure_dmma(int32_t device, double *dmma_tflops);
  * four iteration sums.  0 when nranks == 1.  Either pointer may be NULL.  Collective. */
 int fea_gpu_bench_comm(fea_gpu_handle h, int32_t reps, double *halo_ms, double *allreduce_ms);
 /* tuning knobs: "gather_mode" (9 = nine lanes per block, the default; 1 = one lane per block),
- * "pcg_variant" (0 = classic two-reduction PCG, 1 = single-reduction, -1 = automatic: 1 iff nranks > 1),
- * "pcg_overlap" (1 = halo exchange beside the interior SpMV slices; default 0), "pcg_batch" (iterations
+ * "pcg_variant" (0 = classic two-reduction PCG, the default; 1 = single-reduction),
+ * "pcg_overlap" (1 = halo exchange beside the interior SpMV slices; default 0),
+ * "precond" (0 = Jacobi, the default; 1 = Chebyshev-accelerated Jacobi z = p_d(D^-1 A) D^-1 r -- what the
+ * host layer selects for a task file's PCG_ILU: several times fewer iterations and reductions for about
+ * the same number of matrix products), "cheb_degree" (default 4), "cheb_ratio" (the polynomial targets
+ * [lmax / ratio, lmax] of D^-1 A, lmax from a power iteration; default 100), "pcg_batch" (iterations
  * queued between host convergence checks), "pcg_stall" (iterations without a new best
  * ||r|| before PCG declares the rounding floor; 0 = automatic, max(500, 50 n^(1/3))) */
 int fea_gpu_set_param(fea_gpu_handle h, const char *name, double value);
