@@ -847,6 +847,18 @@ extern "C" int fea_gpu_save_nodes(fea_gpu_handle c) {
   CU(cudaMemcpyAsync(c->x_saved, c->x, sizeof(double) * nl3, cudaMemcpyDeviceToDevice, c->stream));
   return FEA_GPU_OK;
 }
+extern "C" int fea_gpu_extrapolate_nodes(fea_gpu_handle c, double alpha) {
+  GROUP(c, fea_gpu_extrapolate_nodes(ci, alpha));
+  CHECK_H(c);
+  if (!c->x_saved) {
+    g_err = "no saved nodes";
+    return FEA_GPU_ERR_ARG;
+  }
+  const int n = 3 * c->n_local;     // ghosts included: both arrays hold consistent ghost values
+  fea::extrapolate_kernel<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, c->stream>>>(n, alpha, c->x, c->x_saved);
+  LAUNCHED();
+  return FEA_GPU_OK;
+}
 extern "C" int fea_gpu_restore_nodes(fea_gpu_handle c) {
   GROUP(c, fea_gpu_restore_nodes(ci));
   CHECK_H(c);

@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -127,9 +129,23 @@ static int plan_threads(int nranks) {
   return std::max(1, std::min(32, cores / std::max(1, nranks)));
 }
 
+struct PhaseTimer {   // FEA_PLAN_TIMING=1: where the host planning time goes (stderr)
+  bool on = getenv("FEA_PLAN_TIMING") != nullptr;
+  double t0 = omp_get_wtime();
+  int rank;
+  explicit PhaseTimer(int r) : rank(r) {}
+  void lap(const char *what) {
+    if (!on) return;
+    const double t = omp_get_wtime();
+    fprintf(stderr, "[plan rank %d] %-28s %.3f s\n", rank, what, t - t0);
+    t0 = t;
+  }
+};
+
 void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
                 const int32_t *conn, int rank, int nranks) {
   omp_set_num_threads(plan_threads(nranks));
+  PhaseTimer tm(rank);
   if (n_nodes <= 0 || n_elems <= 0 || !X0 || !conn) throw std::runtime_error("empty mesh");
   if (rank < 0 || nranks < 1 || rank >= nranks) throw std::runtime_error("bad rank/nranks");
   for (int64_t k = 0; k < (int64_t)n_elems * NEN; ++k)
@@ -140,7 +156,9 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
   p.n_elems_global = n_elems;
   double box_hi[3];
   const MortonBox box = bounding_box(n_nodes, X0, box_hi);
+  tm.lap("checks + bounding box");
   partition_nodes(p, n_nodes, X0, nranks, box);
+  tm.lap("partition + numbering");
   const std::vector<int32_t> &owner = p.owner;
   const std::vector<int32_t> &pos = p.pos_in_owner;
 
@@ -200,6 +218,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     p.elem_owned[(size_t)le] = owner[(size_t)c[0]] == rank;
   }
 
+  tm.lap("local elements + nodes");
   // ---- node -> (element, local node) lists for owned nodes (residual gather) ---
   const int32_t n_own = p.n_own;
   p.rptr.assign((size_t)n_own + 1, 0);
@@ -223,6 +242,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
       }
   }
 
+  tm.lap("residual lists");
   // ---- block pattern of the owned rows ---------------------------------------
   p.browptr.assign((size_t)n_own + 1, 0);
   std::vector<int32_t> rowlen((size_t)n_own, 0);
@@ -303,6 +323,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
     }
   }
 
+  tm.lap("pattern + gather map");
   // ---- SELL-32-sigma layout of the same pattern -----------------------------------
   {
     std::vector<int32_t> perm((size_t)n_own);
@@ -372,6 +393,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
       }
   }
 
+  tm.lap("SELL layout");
   // ---- halo lists ---------------------------------------------------------------
   p.nbr_rank.clear();
   p.send_ptr.assign(1, 0);
@@ -412,6 +434,7 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
       p.recv_ptr.push_back(ghost_pos);
     }
   }
+  tm.lap("halo lists");
 }
 
 }  // namespace fea

@@ -757,6 +757,15 @@ __global__ void axpy_kernel(int n, double alpha, const double *__restrict__ x, d
     y[t] = fma(alpha, x[t], y[t]);
 }
 
+// x <- x + alpha (x - x_saved), x_saved <- the old x: secant predictor of a load sequence with equal increments
+__global__ void extrapolate_kernel(int n, double alpha, double *__restrict__ x, double *__restrict__ xs) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double cur = x[t];
+    x[t] = fma(alpha, cur - xs[t], cur);
+    xs[t] = cur;
+  }
+}
+
 // x[dof] += lambda * value for the (pre-aggregated) prescribed DOFs (fea_solver.c:1259-1266)
 __global__ void increment_kernel(int n, const int32_t *__restrict__ dof, const double *__restrict__ val,
                                  double lambda, double *__restrict__ x) {

@@ -28,7 +28,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "fea_gpu_create", "fea_gpu_create_multi", "fea_gpu_destroy", "fea_gpu_nccl_unique_id", "fea_gpu_last_error",
     "fea_gpu_set_nodes", "fea_gpu_get_nodes", "fea_gpu_apply_increment", "fea_gpu_update_nodes",
-    "fea_gpu_update_nodes_scaled", "fea_gpu_save_nodes", "fea_gpu_restore_nodes",
+    "fea_gpu_update_nodes_scaled", "fea_gpu_save_nodes", "fea_gpu_restore_nodes", "fea_gpu_extrapolate_nodes",
     "fea_gpu_update_state", "fea_gpu_assemble_stiffness", "fea_gpu_assemble_residual",
     "fea_gpu_assemble_all", "fea_gpu_apply_bc", "fea_gpu_save_stiffness", "fea_gpu_restore_stiffness",
     "fea_gpu_solve", "fea_gpu_dot_R_u", "fea_gpu_spmv", "fea_gpu_get_state", "fea_gpu_get_forces",
@@ -246,6 +246,10 @@ class FeaGpu:
     def update_nodes(self): self._simple("update_nodes")
     def save_nodes(self): self._simple("save_nodes")
     def restore_nodes(self): self._simple("restore_nodes")
+
+    def extrapolate_nodes(self, alpha=1.0):
+        lib().fea_gpu_extrapolate_nodes.argtypes = [C.c_void_p, C.c_double]
+        _check(lib().fea_gpu_extrapolate_nodes(self.h, float(alpha)))
 
     def update_nodes_scaled(self, eta):
         lib().fea_gpu_update_nodes_scaled.argtypes = [C.c_void_p, C.c_double]

@@ -110,6 +110,11 @@ int fea_gpu_update_nodes_scaled(fea_gpu_handle h, double eta);
  * roll-back of a load increment that inverted elements (host/fea_solver.c: solve) */
 int fea_gpu_save_nodes(fea_gpu_handle h);
 int fea_gpu_restore_nodes(fea_gpu_handle h);
+/* nodes_p <- nodes_p + alpha (nodes_p - saved), saved <- the old nodes_p.  With the nodes of the previous
+ * increment saved and equal increments, alpha = 1 moves the prescribed nodes by exactly one more increment
+ * (what solver_update_nodes_with_bc(self, 1) does, fea_solver.c:168) and gives the interior a secant guess
+ * instead of leaving it behind: same equilibrium, fewer Newton iterations (tools/load_sequence.py). */
+int fea_gpu_extrapolate_nodes(fea_gpu_handle h, double alpha);
 
 /* ---- element phase ----------------------------------------------------- */
 

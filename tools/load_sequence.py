@@ -1,6 +1,11 @@
 """Full-Newton load sequence on a Kuhn block under torchrun (tools; results go to profiles/).
 
-    python -m torch.distributed.run --nproc-per-node N ... tools/load_sequence.py <n> <increments> [model]
+    python -m torch.distributed.run --nproc-per-node N ... tools/load_sequence.py <n> <increments> [model] [bc_style]
+    env: SEQ_DY (increment, default 0.2 = 20 % of a cell), SEQ_LIN_TOL (PCG tolerance, default 1e-12),
+         SEQ_PREDICTOR=1 (start every increment from x + (x - x_previous_increment): the boundary nodes move
+         by the same increment every time, so this is the reference's boundary move plus a secant guess for the
+         interior; the equilibrium Newton converges to is the same, it just starts closer),
+         SEQ_CHECK_EVERY (sigma check / log line every k increments, default 1)
 
 Unit-cube cells, "analytical" boundary set (the homogeneous uniaxial state is the exact solution,
 exact-solutions/uniaxial) with the rigid rotation about y removed (bc_style 2; style 0 = exactly
@@ -39,7 +44,10 @@ def closed_form(k1, lam=100.0, mu=100.0):
 
 L = float(n)
 t0 = time.time()
-DY = 0.2   # per increment: 20 % of a cell, the ratio of the shipped bricks (0.05 on 0.25-size cells)
+DY = float(os.environ.get("SEQ_DY", "0.2"))   # per increment; default 20 % of a cell, the ratio of the shipped bricks (0.05 on 0.25-size cells)
+LIN_TOL = float(os.environ.get("SEQ_LIN_TOL", "1e-12"))
+PREDICTOR = os.environ.get("SEQ_PREDICTOR", "0") == "1"
+CHECK_EVERY = int(os.environ.get("SEQ_CHECK_EVERY", "1"))
 mb = fg.mesh_block(n, n, n, L, L, L, 0.0, bc_style, DY)
 g = fg.FeaGpu(mb["nodes"], mb["conn"], model, 100.0, 100.0, 5, mb["presc_node"], mb["presc_type"], mb["presc_vals"],
               rank=rank, nranks=world, nccl_id=nccl_id, device=int(os.environ.get("LOCAL_RANK", 0)))
@@ -47,26 +55,48 @@ cnt = g.counts()
 if rank == 0:
     print(f"setup {time.time() - t0:.1f}s: {len(mb['conn'])} tets, {3 * len(mb['nodes'])} DOF, {world} rank(s), rank0 {cnt}", flush=True)
 log = []
+sample = np.arange(0, len(mb["conn"]), 53, dtype=np.int32)    # elements whose sigma_yy is checked (every rank: the ones it holds)
+t_all = time.time()
+
+
+def anybad():
+    b = float(g.bad_points())
+    if dist is not None:
+        t = torch.tensor([b], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); b = float(t[0])
+    return b > 0
+
+
 for step in range(1, increments + 1):
     g.sync(); ts = time.time()
-    g.apply_increment(1.0)
+    if PREDICTOR and step > 1:
+        g.extrapolate_nodes(1.0)                 # x <- 2 x_k - x_{k-1} (boundary nodes: exactly one more increment), saved <- x_k
+        g.update_state()
+        if anybad():                             # fall back to the plain boundary move
+            g.restore_nodes(); g.apply_increment(1.0)
+    else:
+        g.save_nodes()
+        g.apply_increment(1.0)
     its, pcg = 0, []
     while True:
         its += 1
         g.assemble_all(True); g.apply_bc(0.0)
-        it, rr, ok = g.solve(1e-12, 40000, fg.X0_ZERO, allow_unconverged=True)
+        it, rr, ok = g.solve(LIN_TOL, 40000, fg.X0_ZERO, allow_unconverged=True)
         tol = g.dot_R_u(); g.update_nodes(); pcg.append(it)
         if rank == 0:
             p = g.phase_ms()
             print(f"  newton {its}: pcg {it} its relres {rr:.2e} exit {p['pcg_exit']} <R,u> {tol:.3e}", flush=True)
         if abs(tol) <= 1e-12 * L ** 3 or its >= 12 or not np.isfinite(tol):
             break
-    g.update_state(); g.sync(); dt = time.time() - ts
+    g.update_state(); g.sync()
+    dt = time.time() - ts
+    if step % CHECK_EVERY and step != increments:
+        if rank == 0:
+            print(json.dumps(dict(step=step, newton_iters=its, pcg_iters=pcg, last_R_dot_u=tol, seconds=dt)), flush=True)
+        continue
     k1 = 1.0 + step * DY / L
     k2, sig = closed_form(k1)
-    F, S = g.get_state()                       # only elements owned by this rank are filled
-    own = np.abs(F[:, 0, 1, 1]) > 0
-    err = float(np.abs(S[own][:, :, 1, 1] / sig - 1).max())
+    F, S, found = g.get_state_elems(sample)    # every rank checks the sampled elements it holds
+    err = float(np.abs(S[found][:, :, 1, 1] / sig - 1).max()) if found.any() else 0.0
     bad = g.bad_points()
     if dist is not None:
         t = torch.tensor([err, float(bad)], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); err, bad = float(t[0]), float(t[1])
@@ -76,6 +106,9 @@ for step in range(1, increments + 1):
     if rank == 0:
         print(json.dumps(rec), flush=True)
 if rank == 0:
-    print("SUMMARY", json.dumps(dict(n=n, tets=len(mb["conn"]), dof=3 * len(mb["nodes"]), ranks=world, model=model, steps=log)), flush=True)
+    print("SUMMARY", json.dumps(dict(n=n, tets=len(mb["conn"]), dof=3 * len(mb["nodes"]), ranks=world, model=model, dy=DY, lin_tol=LIN_TOL,
+                                     predictor=PREDICTOR, total_seconds=time.time() - t_all, final_stretch=1.0 + increments * DY / L,
+                                     worst_sigma_yy_rel_err=max(r["sigma_yy_max_rel_err"] for r in log),
+                                     newton_iters_total=None, steps=log)), flush=True)
 if dist is not None:
     dist.barrier(); dist.destroy_process_group()
