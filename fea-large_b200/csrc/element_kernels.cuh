@@ -45,6 +45,11 @@ constexpr int FLD_SG = 10 * 64, FLD_LM = 13 * 64, FLD_G2 = 14 * 64;
 #define FEA_KE_TMA_STORE 0
 #endif
 constexpr int TILE_D2 = (FEA_KE_TMA_STORE ? 2 : 1) * 9 * 32;   // double2 per warp: the store tile of one block pair (two with the bulk-copy engine)
+// PUSH kernels (direct assembly, fea_plan.cpp "cell layout"): a block pair leaves as two 80-byte cells; the
+// tile row of an element is 11 double2 (10 used): a 44-word stride keeps the 16-byte stores of a quarter warp
+// on distinct banks
+constexpr int PUSH_ROW_D2 = 11;
+constexpr int PUSH_TILE_D2 = PUSH_ROW_D2 * 32;
 
 struct ElemTables {
   double dN[5][3][10];  // shape-function derivatives at the Gauss points (fea_solver.c:503-535)
@@ -64,6 +69,10 @@ struct ElemArgs {
   double *F_soa;               // [ng*9][ne_pad]   (may be null)
   double *S_soa;               // [ng*9][ne_pad]
   double *Ke;                  // [n_elems][KE_STRIDE]  a<=b node-pair blocks, layout in fea_plan.hpp
+  const uint32_t *edest;       // PUSH: [55][ne_pad] cell of block (code, element) | SRC_TRANSPOSE, CELL_NONE = not stored
+  double2 *cells;              // PUSH: [n_cells][5] the cells of the upper slots, layer by layer (fea_plan.cpp)
+  int tile0;                   // first 32-element tile of this launch (chunked assembly)
+  int dbg;                     // diagnostics: 4 = no cell stores
   double *Re;                  // [30][ne_pad]
   unsigned long long *bad;     // count of points with det J <= 0, det F <= 0 or non-finite
 };
@@ -104,18 +113,35 @@ __device__ __forceinline__ void ratio_block(double (&k)[9], double rho) {
   k[7] = fma(rho, k[7], p12);
 }
 
-template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO>
+template <int MODEL, int NG, bool WITH_K, bool WITH_R, bool RATIO, bool PUSH = false>
 __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const ElemTables &c_tab = c_tabs[NG == 5 ? 1 : 0];
   double *fld = reinterpret_cast<double *>(smraw);                       // [NG][FLD_DOUBLES]
   double2 *tiles = reinterpret_cast<double2 *>(fld + NG * FLD_DOUBLES);  // [NG][TILE_D2] store tiles
-  int *goff = reinterpret_cast<int *>(tiles + NG * TILE_D2);             // [9][32] store offsets
+  int *goff = reinterpret_cast<int *>(tiles + NG * (PUSH ? PUSH_TILE_D2 : TILE_D2));   // [9][32] store offsets
+  uint32_t *dsm = reinterpret_cast<uint32_t *>(goff + 9 * 32);          // PUSH: [55][32] cells of this CTA's blocks
   const int lane = threadIdx.x & 31;
   const int gp = threadIdx.x >> 5;
-  const int e0 = blockIdx.x * ELEMS_PER_CTA;
+  const int e0 = (A.tile0 + blockIdx.x) * ELEMS_PER_CTA;
   const int e = e0 + lane;
   const bool live = e < A.n_elems;
+  if (PUSH) {
+    // where this CTA's 32 x 55 blocks go: fetched now, beside the node loads of phase 0, and first needed in phase B
+    // (read straight from global memory at the point of use they cost a DRAM round trip per block pair: 38 % of
+    // the kernel's stall samples, profiles/r2_push_ncu_summary.md)
+    uint32_t d[(NTRI + NG - 1) / NG];
+#pragma unroll
+    for (int i = 0; i < (NTRI + NG - 1) / NG; ++i) {
+      const int code = gp + i * NG;
+      d[i] = (live && code < NTRI) ? A.edest[(size_t)code * A.ne_pad + e] : CELL_NONE;
+    }
+#pragma unroll
+    for (int i = 0; i < (NTRI + NG - 1) / NG; ++i) {
+      const int code = gp + i * NG;
+      if (code < NTRI) dsm[code * 32 + lane] = d[i];
+    }
+  }
 
   // ------------------------------ phase 0 ------------------------------------
   // the NG warps of the CTA fetch the 10 nodes of the 32 elements once (coalesced connectivity,
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
       }
     }
   }
-  if (WITH_K && gp == 0) {
+  if (WITH_K && !PUSH && gp == 0) {
     // where the 16-byte pieces of a block pair go: piece f = 32 it + lane of a warp's
     // [32 elements][9 double2] tile belongs to element f / 9 (same table for every warp and pair)
 #pragma unroll
@@ -288,7 +314,7 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
 #define G2D(q, b) fld[(q)*FLD_DOUBLES + FLD_G2 + (b)*32 + lane]
 
   if (WITH_K || WITH_R) {
-    double2 *tile = tiles + gp * TILE_D2;
+    double2 *tile = tiles + gp * (PUSH ? PUSH_TILE_D2 : TILE_D2);
     const int n_here = min(ELEMS_PER_CTA, A.n_elems - e0);
     unsigned vmask = 0;   // bit it: piece 32 it + lane belongs to an element that exists
 #pragma unroll
@@ -344,6 +370,12 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
         if (WITH_K)
         for (int b = a; b < 10; b += 2) {
           const bool two = b + 1 < 10;   // warp-uniform
+          uint32_t d0 = CELL_NONE, d1 = CELL_NONE;
+          if (PUSH) {   // where this element's two blocks go (the blocks of a pair have consecutive codes, fea_plan.hpp)
+            const uint32_t *dp = dsm + ke_code(a, b) * 32 + lane;
+            d0 = dp[0];
+            if (two) d1 = dp[32];
+          }
           double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -381,9 +413,42 @@ __global__ void __launch_bounds__(NG * 32, 2) element_kernel(ElemArgs A) {
           k1[0] += s1;
           k1[4] += s1;
           k1[8] += s1;
+          if (PUSH) {
+            // Each thread parks its blocks -- transposed where the slot wants K_e[b][a] -- as 80-byte cells in its row
+            // of the warp's tile; the warp then writes cell by cell, five consecutive lanes per cell, the cell index
+            // handed over by shuffle from the lane that owns the element.
+            double2 *t = tile + lane * PUSH_ROW_D2;
+            {
+              const bool tr = (d0 >> 31) != 0;
+              t[0] = make_double2(k0[0], tr ? k0[3] : k0[1]);
+              t[1] = make_double2(tr ? k0[6] : k0[2], tr ? k0[1] : k0[3]);
+              t[2] = make_double2(k0[4], tr ? k0[7] : k0[5]);
+              t[3] = make_double2(tr ? k0[2] : k0[6], tr ? k0[5] : k0[7]);
+              t[4] = make_double2(k0[8], 0.0);
+            }
+            if (two) {
+              const bool tr = (d1 >> 31) != 0;
+              t[5] = make_double2(k1[0], tr ? k1[3] : k1[1]);
+              t[6] = make_double2(tr ? k1[6] : k1[2], tr ? k1[1] : k1[3]);
+              t[7] = make_double2(k1[4], tr ? k1[7] : k1[5]);
+              t[8] = make_double2(tr ? k1[2] : k1[6], tr ? k1[5] : k1[7]);
+              t[9] = make_double2(k1[8], 0.0);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 10; ++it) {
+              if (it >= 5 && !two) break;
+              const int sel = it / 5, f = (it - 5 * sel) * 32 + lane, le = f / 5, part = f - 5 * le;
+              const uint32_t d = __shfl_sync(0xffffffffu, sel ? d1 : d0, le);
+              const double2 v = tile[le * PUSH_ROW_D2 + sel * 5 + part];
+              if (d != CELL_NONE && !(A.dbg & 4)) A.cells[(size_t)(d & 0x7fffffffu) * 5 + part] = v;
+            }
+            __syncwarp();
+            continue;
+          }
 #if FEA_KE_INTERLEAVED
           if (live) {
-            double2 *dst2 = reinterpret_cast<double2 *>(A.Ke + (size_t)blockIdx.x * (32 * KE_STRIDE)) +
+            double2 *dst2 = reinterpret_cast<double2 *>(A.Ke + (size_t)(e0 / ELEMS_PER_CTA) * (32 * KE_STRIDE)) +
                             (size_t)((100 * pr + 9 * ke_pos(a, b)) >> 1) * 32 + lane;
             dst2[0 * 32] = make_double2(k0[0], k0[1]);
             dst2[1 * 32] = make_double2(k0[2], k0[3]);

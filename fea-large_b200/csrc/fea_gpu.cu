@@ -14,6 +14,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -104,6 +105,21 @@ struct fea_gpu_ctx {
   int gather_threads = 128;
   bool elem_ratio = true;          // A5: use the lambda/mu form of the block (set_param "elem_ratio" 0 = generic)
   int gather_split = 8;            // CTAs per slice (L2 footprint of the gather, sparse_kernels.cuh)
+  // direct (push) assembly (gather_mode 2): cells of the upper slots written by the element kernel itself
+  uint16_t *cmeta = nullptr;
+  int32_t *ccell = nullptr, *cmirror = nullptr, *col_order = nullptr;
+  uint32_t *edest = nullptr;
+  double2 *cells = nullptr;
+  int n_cols_active = 0;
+  int cells_dbg = 0;               // diagnostics (tools/push_ab.py): 1 no mirror stores, 2 no own stores, 4 no cell stores in the element kernel
+  int chunk_tiles = 0;             // 0 = one element launch + one gather launch; > 0 = chunks of that many 32-element tiles
+  std::vector<int32_t> chunk_cols; // [chunks + 1] prefix of col_order each chunk may gather
+  int chunk_cols_for = -1;         // chunk_tiles the list was built for
+  cudaStream_t asm_stream = nullptr;   // the gathers of a chunked assembly run beside the next chunk's elements
+  std::vector<cudaEvent_t> chunk_ev;
+  struct AsmGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
+  std::map<int, AsmGraph> asm_graphs;  // captured chunk sequences, one per (residual, Dirichlet, chunk size) variant
+  cudaEvent_t ev_asm = nullptr;
   int gather_mode = 1;             // 1 = lane per slot (gather_blocks_kernel, default), 9 = nine lanes per block (gather_blocks9_kernel: 41 % fewer L1 sectors, same time -- DESIGN 4)
   bool gather9_ok = false;         // the uploaded lists satisfy what gather_blocks9_kernel assumes
 
@@ -363,6 +379,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   if (const char *s = getenv("FEA_GATHER_THREADS")) fea_gpu_set_param(c, "gather_threads", atof(s));
   if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
   if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
+  if (const char *s = getenv("FEA_CHUNK_TILES")) fea_gpu_set_param(c, "chunk_tiles", atof(s));
   if (const char *s = getenv("FEA_PCG_VARIANT")) fea_gpu_set_param(c, "pcg_variant", atof(s));
   if (const char *s = getenv("FEA_PCG_OVERLAP")) fea_gpu_set_param(c, "pcg_overlap", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
@@ -538,7 +555,7 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   const size_t n3 = 3 * (size_t)c->n_own, nl3 = 3 * (size_t)c->n_local;
   TRY(dev_alloc(&c->F_soa, (size_t)c->ng * 9 * c->ne_pad));
   TRY(dev_alloc(&c->S_soa, (size_t)c->ng * 9 * c->ne_pad));
-  TRY(dev_alloc(&c->Ke, (size_t)c->ne_pad * fea::KE_STRIDE));   // ne_pad: whole CTAs of 32 elements
+  // the K_e staging (pull gathers) or the cells (direct assembly) are allocated on first use: ensure_ke / ensure_cells
   TRY(dev_alloc(&c->Re, (size_t)30 * c->ne_pad));
   TRY(dev_alloc(&c->vals, (size_t)c->n_slots * 9));
   TRY(dev_alloc(&c->R, n3));
@@ -696,7 +713,8 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->cptr, c->rptr, c->rsrc, c->sdiag, c->csrc, c->vals, c->vals_saved, c->R, c->u,
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->partials_b, c->counters, c->ctl, c->scalar, c->bad,
-                  c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->cz, c->cd, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound};
+                  c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->cz, c->cd, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound,
+                  c->cmeta, c->ccell, c->cmirror, c->col_order, c->edest, c->cells};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -719,6 +737,10 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
   if (c->tm_a) cudaEventDestroy(c->tm_a);
   if (c->tm_b) cudaEventDestroy(c->tm_b);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
+  for (auto &kv : c->asm_graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (c->ev_asm) cudaEventDestroy(c->ev_asm);
+  if (c->asm_stream) cudaStreamDestroy(c->asm_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -874,25 +896,84 @@ extern "C" int fea_gpu_restore_nodes(fea_gpu_handle c) {
 // element pass
 
 template <int MODEL, int NG, bool RATIO>
-static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args) {
-  const int grid = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
-  const size_t smem = sizeof(double) * NG * fea::FLD_DOUBLES + sizeof(double2) * NG * fea::TILE_D2 + sizeof(int) * 9 * 32;
-#define FEA_LAUNCH(K, Rr)                                                                          \
+static int launch_element(fea_gpu_ctx *c, bool with_k, bool with_r, const fea::ElemArgs &args, int n_tiles) {
+  const int grid = n_tiles;
+  const bool push = with_k && args.cells != nullptr;
+  const size_t smem = sizeof(double) * NG * fea::FLD_DOUBLES +
+                      sizeof(double2) * NG * (push ? fea::PUSH_TILE_D2 : fea::TILE_D2) + sizeof(int) * 9 * 32 +
+                      (push ? sizeof(uint32_t) * fea::NTRI * 32 : 0);
+#define FEA_LAUNCH(K, Rr, P)                                                                       \
   do {                                                                                             \
-    auto kern = fea::element_kernel<MODEL, NG, K, Rr, RATIO>;                                      \
+    auto kern = fea::element_kernel<MODEL, NG, K, Rr, RATIO, P>;                                   \
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kern<<<grid, NG * 32, smem, c->stream>>>(args);                                                \
   } while (0)
-  if (with_k && with_r) FEA_LAUNCH(true, true);
-  else if (with_k) FEA_LAUNCH(true, false);
-  else if (with_r) FEA_LAUNCH(false, true);
-  else FEA_LAUNCH(false, false);
+  if (push && with_r) FEA_LAUNCH(true, true, true);
+  else if (push) FEA_LAUNCH(true, false, true);
+  else if (with_k && with_r) FEA_LAUNCH(true, true, false);
+  else if (with_k) FEA_LAUNCH(true, false, false);
+  else if (with_r) FEA_LAUNCH(false, true, false);
+  else FEA_LAUNCH(false, false, false);
 #undef FEA_LAUNCH
   LAUNCHED();
   return FEA_GPU_OK;
 }
 
-static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
+// device side of the cell layout, on first use of gather_mode 2
+static int ensure_cells(fea_gpu_ctx *c) {
+  if (c->cells) return FEA_GPU_OK;
+  const fea::Plan &pl = c->plan;
+  TRY(dev_upload(&c->cmeta, pl.cmeta, c->stream));
+  TRY(dev_upload(&c->ccell, pl.ccell, c->stream));
+  TRY(dev_upload(&c->cmirror, pl.cmirror, c->stream));
+  TRY(dev_upload(&c->col_order, pl.col_order, c->stream));
+  TRY(dev_upload(&c->edest, pl.edest, c->stream));
+  c->n_cols_active = (int)pl.col_order.size();
+  TRY(dev_alloc(&c->cells, (size_t)std::max<int64_t>(pl.n_cells(), 1) * 5));
+  CU(cudaStreamCreateWithFlags(&c->asm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
+  CU(cudaStreamSynchronize(c->stream));
+  return FEA_GPU_OK;
+}
+static int ensure_ke(fea_gpu_ctx *c) {
+  if (c->Ke) return FEA_GPU_OK;
+  return dev_alloc(&c->Ke, (size_t)c->ne_pad * fea::KE_STRIDE);   // ne_pad: whole CTAs of 32 elements
+}
+
+// prefix of col_order every chunk of `chunk_tiles` element tiles may gather: the columns whose last
+// contributing element lies before the end of the chunk
+static void build_chunks(fea_gpu_ctx *c) {
+  if (c->chunk_cols_for == c->chunk_tiles) return;
+  const fea::Plan &pl = c->plan;
+  const int n_tiles = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
+  const int n_chunks = cdiv(n_tiles, c->chunk_tiles);
+  c->chunk_cols.assign((size_t)n_chunks + 1, 0);
+  size_t k = 0;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int64_t e_end = std::min<int64_t>((int64_t)(ch + 1) * c->chunk_tiles * fea::ELEMS_PER_CTA, c->n_elems);
+    while (k < pl.col_order.size() && pl.col_ready[(size_t)pl.col_order[k]] < e_end) ++k;
+    c->chunk_cols[(size_t)ch + 1] = (int32_t)k;
+  }
+  while ((int)c->chunk_ev.size() < n_chunks) {
+    cudaEvent_t ev;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    c->chunk_ev.push_back(ev);
+  }
+  c->chunk_cols_for = c->chunk_tiles;
+}
+
+static int launch_gather_cells(fea_gpu_ctx *c, int col0, int col1, bool with_bc, cudaStream_t st) {
+  if (col1 <= col0) return FEA_GPU_OK;
+  constexpr int W = 4;
+  fea::gather_cells_kernel<W><<<cdiv(col1 - col0, W), W * 32, 0, st>>>(
+      col1 - col0, c->col_order + col0, c->ccell, c->cmeta, c->cmirror, c->cells, c->vals, with_bc ? c->sflag : nullptr, c->cells_dbg);
+  LAUNCHED();
+  return FEA_GPU_OK;
+}
+
+static int element_launch(fea_gpu_ctx *c, bool with_k, bool with_r, fea::ElemArgs &a, int tile0, int n_tiles);
+
+static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc = false, bool *gathered = nullptr) {
   fea::ElemArgs a;
   a.n_elems = c->n_elems;
   a.ne_pad = c->ne_pad;
@@ -903,22 +984,83 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r) {
   a.mu = c->mu;
   a.F_soa = c->F_soa;
   a.S_soa = c->S_soa;
+  const bool push = with_k && c->gather_mode == 2;
+  if (push) TRY(ensure_cells(c));
+  else if (with_k) TRY(ensure_ke(c));
   a.Ke = c->Ke;
+  a.edest = push ? c->edest : nullptr;
+  a.cells = push ? c->cells : nullptr;
+  a.dbg = c->cells_dbg;
+  a.tile0 = 0;
   a.Re = c->Re;
   a.bad = c->bad;
   CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
+  const int n_tiles = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
+  if (gathered) *gathered = false;
+  if (push && gathered && c->chunk_tiles > 0 && c->chunk_tiles < n_tiles) {
+    // Chunked assembly: the element kernel runs chunk by chunk on the context's stream, and the columns that a
+    // chunk completes are gathered on a second stream beside the next chunk's elements -- their cells were
+    // written microseconds ago and are read back from L2 instead of HBM.
+    build_chunks(c);
+    phase_begin(c, PH_ELEM);
+    // The ~2 x chunks launches and their cross-stream dependencies are captured once per variant into a CUDA
+    // graph: issued one by one from the host they cost more than the kernels take.
+    const int key = (with_r ? 1 : 0) | (chunk_bc ? 2 : 0) | (c->cells_dbg << 2) | (c->chunk_tiles << 8);
+    auto it = c->asm_graphs.find(key);
+    if (it == c->asm_graphs.end()) {
+      const int n_chunks = (int)c->chunk_cols.size() - 1;
+      const int64_t l0 = g_launches.load();
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = FEA_GPU_OK;
+      auto body = [&]() -> int {
+        CU(cudaEventRecord(c->ev_asm, c->stream));
+        CU(cudaStreamWaitEvent(c->asm_stream, c->ev_asm, 0));
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int t0 = ch * c->chunk_tiles, nt = std::min(c->chunk_tiles, n_tiles - t0);
+          TRY(element_launch(c, with_k, with_r, a, t0, nt));
+          CU(cudaEventRecord(c->chunk_ev[(size_t)ch], c->stream));
+          CU(cudaStreamWaitEvent(c->asm_stream, c->chunk_ev[(size_t)ch], 0));
+          TRY(launch_gather_cells(c, c->chunk_cols[(size_t)ch], c->chunk_cols[(size_t)ch + 1], chunk_bc, c->asm_stream));
+        }
+        CU(cudaEventRecord(c->ev_asm, c->asm_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_asm, 0));
+        return FEA_GPU_OK;
+      };
+      rc = body();
+      const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      if (rc != FEA_GPU_OK) return rc;
+      CU(ce);
+      fea_gpu_ctx::AsmGraph ag;
+      CU(cudaGraphInstantiate(&ag.exec, graph, 0));
+      CU(cudaGraphDestroy(graph));
+      ag.launches = (int)(g_launches.load() - l0);   // kernels per graph launch (the capture itself counted them once)
+      it = c->asm_graphs.emplace(key, ag).first;
+    }
+    CU(cudaGraphLaunch(it->second.exec, c->stream));
+    g_launches.fetch_add(it->second.launches, std::memory_order_relaxed);
+    phase_end(c, PH_ELEM);
+    *gathered = true;   // the stiffness gather is done
+    return FEA_GPU_OK;
+  }
   phase_begin(c, PH_ELEM);
+  const int rc = element_launch(c, with_k, with_r, a, 0, n_tiles);
+  phase_end(c, PH_ELEM);
+  return rc;
+}
+
+static int element_launch(fea_gpu_ctx *c, bool with_k, bool with_r, fea::ElemArgs &a, int tile0, int n_tiles) {
+  a.tile0 = tile0;
   int rc;
   // A5 with mu != 0: lam' / mu' is the same at every Gauss point (element_kernels.cuh, RATIO)
   a.rho = c->mu != 0.0 ? c->lambda / c->mu : 0.0;
   const bool ratio = c->model == FEA_MODEL_A5 && c->mu != 0.0 && std::isfinite(a.rho) && c->elem_ratio;
   if (c->model == FEA_MODEL_A5 && ratio)
-    rc = c->ng == 5 ? launch_element<0, 5, true>(c, with_k, with_r, a) : launch_element<0, 4, true>(c, with_k, with_r, a);
+    rc = c->ng == 5 ? launch_element<0, 5, true>(c, with_k, with_r, a, n_tiles) : launch_element<0, 4, true>(c, with_k, with_r, a, n_tiles);
   else if (c->model == FEA_MODEL_A5)
-    rc = c->ng == 5 ? launch_element<0, 5, false>(c, with_k, with_r, a) : launch_element<0, 4, false>(c, with_k, with_r, a);
+    rc = c->ng == 5 ? launch_element<0, 5, false>(c, with_k, with_r, a, n_tiles) : launch_element<0, 4, false>(c, with_k, with_r, a, n_tiles);
   else
-    rc = c->ng == 5 ? launch_element<1, 5, false>(c, with_k, with_r, a) : launch_element<1, 4, false>(c, with_k, with_r, a);
-  phase_end(c, PH_ELEM);
+    rc = c->ng == 5 ? launch_element<1, 5, false>(c, with_k, with_r, a, n_tiles) : launch_element<1, 4, false>(c, with_k, with_r, a, n_tiles);
   return rc;
 }
 
@@ -935,6 +1077,11 @@ static fea::SellMat sell_mat(fea_gpu_ctx *c) {
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
   const uint8_t *pf = with_bc ? c->sflag : nullptr;
+  if (c->gather_mode == 2) {
+    TRY(launch_gather_cells(c, 0, c->n_cols_active, with_bc, c->stream));
+    phase_end(c, PH_GATHER_K);
+    return FEA_GPU_OK;
+  }
   {
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
@@ -970,8 +1117,9 @@ extern "C" int fea_gpu_update_state(fea_gpu_handle c) {
 extern "C" int fea_gpu_assemble_stiffness(fea_gpu_handle c) {
   GROUP(c, fea_gpu_assemble_stiffness(ci));
   CHECK_H(c);
-  TRY(element_pass(c, true, false));
-  return gather_stiffness(c, false);
+  bool gathered = false;
+  TRY(element_pass(c, true, false, false, &gathered));
+  return gathered ? FEA_GPU_OK : gather_stiffness(c, false);
 }
 extern "C" int fea_gpu_assemble_residual(fea_gpu_handle c) {
   GROUP(c, fea_gpu_assemble_residual(ci));
@@ -983,8 +1131,9 @@ extern "C" int fea_gpu_assemble_all(fea_gpu_handle c, int32_t flags) {
   GROUP(c, fea_gpu_assemble_all(ci, flags));
   CHECK_H(c);
   const bool with_k = (flags & FEA_ASSEMBLE_STIFFNESS) != 0, fuse_bc = (flags & FEA_ASSEMBLE_FUSE_BC) != 0;
-  TRY(element_pass(c, with_k, true));
-  if (with_k) TRY(gather_stiffness(c, fuse_bc));
+  bool gathered = false;
+  TRY(element_pass(c, with_k, true, fuse_bc, &gathered));
+  if (with_k && !gathered) TRY(gather_stiffness(c, fuse_bc));
   if (!fuse_bc) return gather_residual(c);
   // solver_apply_prescribed_bc(self, 0) folded into the two gathers: rows and columns of prescribed
   // DOFs cancelled keeping the diagonal, their right-hand side rows zero (fea_solver.c:1244-1257)
@@ -1580,8 +1729,30 @@ extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, dou
     return FEA_GPU_ERR_ARG;
   }
   double st[fea::KE_STRIDE];
-  CU(cudaMemcpyAsync(st, c->Ke + (size_t)le * fea::KE_STRIDE, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (c->gather_mode == 2) {
+    // direct assembly: the element's blocks sit in the cells of their slots (blocks of rows owned by another
+    // rank are not stored at all: they read as zero here)
+    if (!c->cells) {
+      g_err = "no stiffness assembled yet";
+      return FEA_GPU_ERR_ARG;
+    }
+    std::memset(st, 0, sizeof(st));
+    for (int code = 0; code < fea::NTRI; ++code) {
+      const uint32_t d = c->plan.edest[(size_t)code * c->ne_pad + le];
+      if (d == fea::CELL_NONE) continue;
+      double cell[9], *blk = st + 100 * (code / 11) + 9 * (code % 11);
+      CU(cudaMemcpyAsync(cell, c->cells + (size_t)(d & 0x7fffffffu) * 5, sizeof(cell), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      for (int k = 0; k < 9; ++k) blk[k] = (d >> 31) ? cell[(k % 3) * 3 + k / 3] : cell[k];
+    }
+  } else {
+    if (!c->Ke) {
+      g_err = "no stiffness assembled yet";
+      return FEA_GPU_ERR_ARG;
+    }
+    CU(cudaMemcpyAsync(st, c->Ke + (size_t)le * fea::KE_STRIDE, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   for (int a = 0; a < fea::NEN; ++a)
     for (int b = a; b < fea::NEN; ++b) {
       const int code = fea::ke_code(a, b);
@@ -1692,7 +1863,8 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
     h2d = sizeof(double) * nl3;
     CU(cudaMemcpyAsync(c->x, c->stage_h, h2d, cudaMemcpyHostToDevice, c->stream));
   }
-  TRY(element_pass(c, with_stiffness != 0, true));
+  bool gathered = false;
+  TRY(element_pass(c, with_stiffness != 0, true, true, &gathered));
   // residual first: its way back to the host (copy stream) overlaps the stiffness gather
   phase_begin(c, PH_GATHER_R);
   fea::gather_residual_kernel<<<cdiv(3 * (int64_t)c->n_own, 256), 256, 0, c->stream>>>(
@@ -1713,7 +1885,7 @@ extern "C" int fea_gpu_step_from_host(fea_gpu_handle c, const double *x, int32_t
     CU(cudaMemcpyAsync(R + 3 * (size_t)c->own_lo, c->io_buf, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
   else
     CU(cudaMemcpyAsync(c->stage_h, c->R, d2h, cudaMemcpyDeviceToHost, c->copy_stream));
-  if (with_stiffness) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
+  if (with_stiffness && !gathered) TRY(gather_stiffness(c, true));   // Dirichlet cancellation fused into the gather
   CU(cudaStreamSynchronize(c->copy_stream));
   CU(cudaStreamSynchronize(c->stream));
   if (!ranged)
@@ -1843,7 +2015,9 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   if (k == "gather_threads" && (v == 128 || v == 256 || v == 512 || v == 1024)) c->gather_threads = v;
   else if (k == "elem_ratio" && (v == 0 || v == 1)) c->elem_ratio = v != 0;
   else if (k == "gather_split" && v >= 1 && v <= 8) c->gather_split = v;
-  else if (k == "gather_mode" && (v == 1 || v == 9)) c->gather_mode = v;
+  else if (k == "gather_mode" && (v == 1 || v == 9 || v == 2)) c->gather_mode = v;
+  else if (k == "chunk_tiles" && v >= 0) c->chunk_tiles = v;
+  else if (k == "cells_dbg" && v >= 0) c->cells_dbg = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else if (k == "pcg_variant" && v >= 0 && v <= 1) c->pcg_variant = v;

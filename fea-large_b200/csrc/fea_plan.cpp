@@ -394,6 +394,114 @@ void build_plan(Plan &p, int32_t n_nodes, int32_t n_elems, const double *X0,
   }
 
   tm.lap("SELL layout");
+  // ---- cell layout of the direct (push) assembly ---------------------------------------------
+  // Upper slots only (column >= row in local numbering; ghost columns come after the owned rows, so every
+  // slot with a ghost column is upper).  A 32-slot SELL column keeps its contributions ("cells", one 3x3
+  // block each, CELL_DOUBLES doubles) as consecutive layers: layer k holds the k-th contribution (ascending
+  // global element id, the reference's accumulation order, fea_solver.c:878-882) of every slot that has
+  // one, the slots ordered by descending contribution count (ties by lane) -- so the same slot sits at the
+  // same position of every layer and a layer is one contiguous run of memory.  The element kernel writes each
+  // K_e block straight into its cell (transposed when the element's node order is the other way round), the
+  // gather adds the layers position by position with fully coalesced loads, and writes the finished block to
+  // its slot and, transposed, to the mirror slot of the lower triangle.
+  {
+    const int64_t n_slots = (int64_t)p.sbcol.size();
+    const int64_t n_cols = n_slots / SELL_C;
+    p.cmeta.assign((size_t)n_slots, 0);
+    p.cmirror.assign((size_t)n_slots, -1);
+    p.ccell.assign((size_t)n_cols + 1, 0);
+    p.col_ready.assign((size_t)n_cols, -1);
+    const int32_t ne_pad = (p.n_elems + 31) / 32 * 32;   // SoA pitch of the element arrays (whole element-kernel CTAs)
+    p.edest.assign((size_t)NTRI * ne_pad, 0xffffffffu);
+    std::vector<int32_t> slot_row((size_t)n_slots, -1);   // row of each real slot
+#pragma omp parallel for schedule(static)
+    for (int32_t s = 0; s < p.n_slices; ++s) {
+      const int32_t width = (p.slice_ptr[(size_t)s + 1] - p.slice_ptr[(size_t)s]) / SELL_C;
+      for (int l = 0; l < SELL_C; ++l) {
+        const int32_t r = p.sell_row[(size_t)s * SELL_C + l];
+        const int32_t len = r >= 0 ? rowlen[(size_t)r] : 0;
+        for (int32_t j = 0; j < std::min(len, width); ++j) slot_row[(size_t)p.slice_ptr[(size_t)s] + (size_t)j * SELL_C + l] = r;
+      }
+    }
+    // cells per column
+    std::vector<int32_t> ncell((size_t)n_cols, 0);
+    bool too_many = false;
+#pragma omp parallel for schedule(static) reduction(|| : too_many)
+    for (int64_t col = 0; col < n_cols; ++col) {
+      int32_t tot = 0;
+      for (int l = 0; l < SELL_C; ++l) {
+        const int64_t slot = col * SELL_C + l;
+        const int32_t r = slot_row[(size_t)slot];
+        if (r < 0 || p.sbcol[(size_t)slot] < r) continue;
+        const int32_t n = p.scptr[(size_t)slot + 1] - p.scptr[(size_t)slot];
+        if (n > CELL_MAX_CONTRIB) too_many = true;
+        tot += n;
+      }
+      ncell[(size_t)col] = tot;
+    }
+    if (too_many) throw std::runtime_error("a node pair is shared by more than 2047 elements");
+    int64_t run = 0;
+    for (int64_t col = 0; col < n_cols; ++col) {
+      p.ccell[(size_t)col] = (int32_t)run;
+      run += ncell[(size_t)col];
+      if (run >= (int64_t)0x7fffffff) throw std::runtime_error("more than 2^31 stiffness cells on one rank");
+    }
+    p.ccell[(size_t)n_cols] = (int32_t)run;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t col = 0; col < n_cols; ++col) {
+      int32_t n[SELL_C], order[SELL_C], rank[SELL_C];
+      for (int l = 0; l < SELL_C; ++l) {
+        const int64_t slot = col * SELL_C + l;
+        const int32_t r = slot_row[(size_t)slot];
+        n[l] = (r < 0 || p.sbcol[(size_t)slot] < r) ? 0 : p.scptr[(size_t)slot + 1] - p.scptr[(size_t)slot];
+        order[l] = l;
+      }
+      std::stable_sort(order, order + SELL_C, [&](int a, int b) { return n[a] > n[b]; });
+      for (int i = 0; i < SELL_C; ++i) rank[order[i]] = i;
+      int32_t layer_base[CELL_MAX_CONTRIB + 2];
+      {
+        int32_t off = p.ccell[(size_t)col];
+        const int32_t kmax = n[order[0]];
+        int m = SELL_C;
+        for (int32_t k = 0; k < kmax; ++k) {
+          while (m > 0 && n[order[m - 1]] <= k) --m;   // slots with more than k contributions
+          layer_base[k] = off;
+          off += m;
+        }
+      }
+      int32_t ready = -1;
+      for (int l = 0; l < SELL_C; ++l) {
+        const int64_t slot = col * SELL_C + l;
+        if (n[l] == 0) continue;
+        p.cmeta[(size_t)slot] = (uint16_t)(n[l] | (rank[l] << CELL_RANK_SHIFT));
+        const int32_t r = slot_row[(size_t)slot], cnode = p.sbcol[(size_t)slot];
+        for (int32_t k = 0; k < n[l]; ++k) {
+          const uint32_t src = p.scsrc[(size_t)p.scptr[(size_t)slot] + (size_t)k];
+          const uint32_t idx = src & 0x7fffffffu;
+          const int32_t e = (int32_t)(idx / NTRI), code = (int32_t)(idx - (uint32_t)e * NTRI);
+          p.edest[(size_t)code * ne_pad + e] = (uint32_t)(layer_base[k] + rank[l]) | (src & SRC_TRANSPOSE);
+          ready = std::max(ready, e);
+        }
+        if (cnode > r && cnode < n_own) {   // mirror slot (cnode, r): binary search in cnode's ascending columns
+          const int32_t lo = p.browptr[(size_t)cnode], hi = p.browptr[(size_t)cnode + 1];
+          const int32_t *f = std::lower_bound(p.bcol.data() + lo, p.bcol.data() + hi, r);
+          const int32_t jm = (int32_t)(f - (p.bcol.data() + lo));
+          const int32_t km = p.row_lane[(size_t)cnode];
+          p.cmirror[(size_t)slot] = 9 * (p.slice_ptr[(size_t)(km / SELL_C)] + jm * SELL_C) + (km % SELL_C);
+        }
+      }
+      p.col_ready[(size_t)col] = ready;
+    }
+    // columns in the order their last contributing element is produced (chunked assembly: a column is
+    // gathered as soon as the element tiles before that point are done, while its cells are still in L2)
+    p.col_order.clear();
+    for (int64_t col = 0; col < n_cols; ++col)
+      if (p.col_ready[(size_t)col] >= 0) p.col_order.push_back((int32_t)col);
+    std::stable_sort(p.col_order.begin(), p.col_order.end(),
+                     [&](int32_t a, int32_t b) { return p.col_ready[(size_t)a] < p.col_ready[(size_t)b]; });
+  }
+
+  tm.lap("cell layout");
   // ---- halo lists ---------------------------------------------------------------
   p.nbr_rank.clear();
   p.send_ptr.assign(1, 0);
@@ -484,6 +592,8 @@ void plan_counts(const Plan &pl, int64_t out[16]) {
   out[9] = pl.n_elems_global;
   out[10] = pl.n_slots();
   out[11] = pl.n_slices;
+  out[12] = pl.n_cells();
+  out[13] = (int64_t)pl.col_order.size();
 }
 }  // namespace fea
 
@@ -527,6 +637,19 @@ extern "C" int fea_plan_sell_arrays(fea_plan_handle p, int32_t *slice_ptr, int32
   copy_out(scptr, pl.scptr);
   copy_out(scsrc, pl.scsrc);
   copy_out(sdiag, pl.sdiag);
+  return FEA_GPU_OK;
+}
+
+extern "C" int fea_plan_cell_arrays(fea_plan_handle p, uint16_t *cmeta, int32_t *ccell, int32_t *cmirror, uint32_t *edest,
+                                    int32_t *col_ready, int32_t *col_order) {
+  if (!p) return FEA_GPU_ERR_ARG;
+  const fea::Plan &pl = p->plan;
+  copy_out(cmeta, pl.cmeta);
+  copy_out(ccell, pl.ccell);
+  copy_out(cmirror, pl.cmirror);
+  copy_out(edest, pl.edest);
+  copy_out(col_ready, pl.col_ready);
+  copy_out(col_order, pl.col_order);
   return FEA_GPU_OK;
 }
 

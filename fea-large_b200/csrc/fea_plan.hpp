@@ -43,6 +43,13 @@ FEA_HD inline int ke_pos(int a, int b) {   // a <= b
 }
 FEA_HD inline int ke_code(int a, int b) { return 11 * (a < NEN - 1 - a ? a : NEN - 1 - a) + ke_pos(a, b); }
 
+// Direct (push) assembly: one cell per contribution to an upper slot, CELL_DOUBLES doubles (the 3x3 block and
+// one pad double, so every cell starts on a 16-byte boundary); layout in fea_plan.cpp ("cell layout")
+constexpr int CELL_DOUBLES = 10;
+constexpr int CELL_MAX_CONTRIB = 2047;  // contributions per slot: low 11 bits of Plan::cmeta
+constexpr int CELL_RANK_SHIFT = 11;     // high 5 bits: position of the slot inside every layer of its column
+constexpr uint32_t CELL_NONE = 0xffffffffu;
+
 constexpr int SELL_C = 32;              // rows per SELL slice = one warp
 constexpr int SELL_SIGMA = 2048;        // rows per length-sorting window
 
@@ -81,6 +88,15 @@ struct Plan {
   std::vector<uint32_t> scsrc;          // [ncontrib]
   std::vector<int32_t> sdiag;           // [n_own] value index of the (0,0) entry of the diagonal block
   int64_t n_slots() const { return (int64_t)sbcol.size(); }
+
+  // direct (push) assembly, see "cell layout" in fea_plan.cpp
+  std::vector<uint16_t> cmeta;          // [n_slots] upper slots: contributions | rank << 11; 0 = lower triangle / padding
+  std::vector<int32_t> ccell;           // [n_slots/32 + 1] first cell of each 32-slot column
+  std::vector<int32_t> cmirror;         // [n_slots] value index of the (0,0) entry of the mirror slot, -1 = none
+  std::vector<uint32_t> edest;          // [55][ne_pad] cell of staged block (code, element) | SRC_TRANSPOSE; CELL_NONE = row not owned
+  std::vector<int32_t> col_ready;       // [n_slots/32] last local element contributing to the column, -1 = no upper slot
+  std::vector<int32_t> col_order;       // columns with upper slots, ascending col_ready
+  int64_t n_cells() const { return ccell.empty() ? 0 : (int64_t)ccell.back(); }
 
   // residual gather map (node -> (element, local node))
   std::vector<int32_t> rptr;            // [n_own+1]

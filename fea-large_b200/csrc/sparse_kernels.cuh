@@ -11,6 +11,8 @@
 #pragma once
 #include <cstdint>
 
+#include "fea_plan.hpp"
+
 namespace fea {
 
 constexpr int RED_THREADS = 256;
@@ -285,6 +287,98 @@ gather_blocks9_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, co
       out[c2 * 32] = a;
     }
     __syncwarp();
+  }
+}
+
+// K3, direct (push) assembly: the element kernel has written every contribution of an upper slot into its cell
+// (fea_plan.cpp, "cell layout").  One warp per 32-slot SELL column: the column's cells are `kmax` consecutive
+// layers, layer k = the k-th contribution of the m_k slots that have one, in the same slot order every layer, so
+// the sum over layers runs position by position on the raw memory image: lane l owns 16-byte units l, l+32, ...
+// of a layer (unit u = double2 `u % 5` of the cell at position u / 5) -- every load instruction of the warp reads
+// one contiguous run (<= 512 bytes), against 32 unrelated 16-byte sectors per load in the pull kernels above.
+// A slot's sum still runs in list order, one add per contribution starting from zero: bit-identical to
+// gather_item.  The finished image is turned round through a [32 cells][10] shared tile (lane = slot again),
+// the Dirichlet flags are applied, and each upper slot stores its block (coalesced along the lanes that are
+// upper) and, transposed, the mirror slot of the lower triangle (K_e is symmetric, so is every partial sum).
+// Lower and padding slots are never written by their own column: padding stays zero from the allocation.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+gather_cells_kernel(int n_cols, const int32_t *__restrict__ col_order, const int32_t *__restrict__ ccell,
+                    const uint16_t *__restrict__ cmeta, const int32_t *__restrict__ cmirror,
+                    const double2 *__restrict__ cells, double *__restrict__ vals,
+                    const uint8_t *__restrict__ sflag /* may be null */, int dbg /* diagnostics: 1 no mirror stores, 2 no own stores */) {
+  __shared__ __align__(16) double tile_s[WARPS][32 * CELL_DOUBLES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x * WARPS + warp;
+  if (w >= n_cols) return;
+  const int col = col_order[w];
+  const size_t slot = (size_t)col * 32 + lane;
+  const unsigned meta = cmeta[slot];
+  const int n = meta & CELL_MAX_CONTRIB, rk = meta >> CELL_RANK_SHIFT;
+  const int kmax = __reduce_max_sync(0xffffffffu, n);
+  const double2 *layer = cells + (size_t)ccell[col] * 5;
+  double2 acc[5];
+#pragma unroll
+  for (int h = 0; h < 5; ++h) acc[h] = make_double2(0.0, 0.0);
+  int k = 0;
+  for (; k + 1 < kmax; k += 2) {   // two layers in flight
+    const int m0 = __popc(__ballot_sync(0xffffffffu, n > k)), m1 = __popc(__ballot_sync(0xffffffffu, n > k + 1));
+    const double2 *l0 = layer, *l1 = layer + 5 * m0;
+    double2 a[5], b[5];
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const int u = lane + 32 * h;
+      a[h] = u < 5 * m0 ? __ldcs(l0 + u) : make_double2(0.0, 0.0);
+      b[h] = u < 5 * m1 ? __ldcs(l1 + u) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const int u = lane + 32 * h;
+      if (u < 5 * m0) { acc[h].x += a[h].x; acc[h].y += a[h].y; }
+      if (u < 5 * m1) { acc[h].x += b[h].x; acc[h].y += b[h].y; }
+    }
+    layer += 5 * (m0 + m1);
+  }
+  if (k < kmax) {
+    const int m0 = __popc(__ballot_sync(0xffffffffu, n > k));
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const int u = lane + 32 * h;
+      if (u < 5 * m0) {
+        const double2 a = __ldcs(layer + u);
+        acc[h].x += a.x;
+        acc[h].y += a.y;
+      }
+    }
+  }
+  double2 *tile2 = reinterpret_cast<double2 *>(tile_s[warp]);
+#pragma unroll
+  for (int h = 0; h < 5; ++h) tile2[lane + 32 * h] = acc[h];
+  __syncwarp();
+  if (n > 0) {
+    const double *mine = tile_s[warp] + rk * CELL_DOUBLES;
+    double v[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = mine[c];
+    const unsigned f = sflag ? sflag[slot] : 0u;   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
+    if (f & 63u) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const int i = c / 3, jj = c % 3;
+        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) v[c] = 0.0;
+      }
+    }
+    double *out = vals + (size_t)col * (32 * 9) + lane;
+    if (!(dbg & 2)) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) out[c * 32] = v[c];
+    }
+    const int mp = (dbg & 1) ? -1 : cmirror[slot];
+    if (mp >= 0) {
+      double *mo = vals + mp;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) mo[c * 32] = v[(c % 3) * 3 + c / 3];
+    }
   }
 }
 

@@ -36,7 +36,7 @@ SYMBOLS = [
     "fea_gpu_counts", "fea_gpu_launch_count", "fea_gpu_timer_start", "fea_gpu_timer_stop",
     "fea_gpu_sync", "fea_gpu_phase_ms", "fea_gpu_bench_spmv", "fea_gpu_measure_peaks",
     "fea_gpu_flush_l2", "fea_gpu_set_param", "fea_gpu_measure_dmma", "fea_gpu_bench_comm", "fea_gpu_host_alloc", "fea_gpu_host_free", "fea_gpu_step_from_host", "fea_plan_create", "fea_plan_destroy", "fea_plan_counts", "fea_plan_arrays",
-    "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_mesh_block", "fea_mesh_cylinder",
+    "fea_plan_node_owner", "fea_plan_sell_arrays", "fea_plan_cell_arrays", "fea_mesh_block", "fea_mesh_cylinder",
 ]
 
 _lib = None
@@ -178,6 +178,19 @@ class Plan:
         f.argtypes = [C.c_void_p] * 7
         _check(f(self.h, *[a.ctypes.data for a in (self.slice_ptr, self.sell_row, self.sbcol, self.scptr,
                                                     self.scsrc, self.sdiag)]))
+
+        self.n_cells, self.n_cols_active = int(cnt[12]), int(cnt[13])
+        ne_pad = (self.n_elems + 31) // 32 * 32
+        self.cmeta = np.empty(self.n_slots, np.uint16)
+        self.ccell = np.empty(self.n_slots // 32 + 1, np.int32)
+        self.cmirror = np.empty(self.n_slots, np.int32)
+        self.edest = np.empty((55, ne_pad), np.uint32)
+        self.col_ready = np.empty(self.n_slots // 32, np.int32)
+        self.col_order = np.empty(self.n_cols_active, np.int32)
+        f = lib().fea_plan_cell_arrays
+        f.argtypes = [C.c_void_p] * 7
+        _check(f(self.h, *[a.ctypes.data for a in (self.cmeta, self.ccell, self.cmirror, self.edest, self.col_ready,
+                                                    self.col_order)]))
 
     def close(self):
         if self.h:

@@ -274,6 +274,15 @@ int fea_plan_node_owner(fea_plan_handle p, int32_t *owner /* [n_nodes] */);
 int fea_plan_sell_arrays(fea_plan_handle p, int32_t *slice_ptr, int32_t *sell_row, int32_t *sbcol,
                          int32_t *scptr, uint32_t *scsrc, int32_t *sdiag);
 
+/* the cell layout of the direct (push) assembly (fea_plan.cpp "cell layout"; any pointer may be NULL; sizes from
+ * fea_plan_counts: [10] slots, [12] cells, [13] columns with upper slots):
+ *   cmeta [slots] contributions | rank << 11 of every upper slot (0 = lower triangle / padding),
+ *   ccell [slots / 32 + 1] first cell of each 32-slot column, cmirror [slots] value index of the mirror slot or -1,
+ *   edest [55][elements rounded up to 32] cell | (1<<31: store transposed) of every staged block, 0xffffffff = none,
+ *   col_ready [slots / 32] last local element contributing (-1 = no upper slot), col_order [.] ascending col_ready */
+int fea_plan_cell_arrays(fea_plan_handle p, uint16_t *cmeta, int32_t *ccell, int32_t *cmirror, uint32_t *edest,
+                         int32_t *col_ready, int32_t *col_order);
+
 /* Kuhn (Freudenthal) 6-tet block, 10-node tets in the reference node order:
  * nx*ny*nz cubes on [0,lx]x[y0,y0+ly]x[0,lz]; nodes (2nx+1)(2ny+1)(2nz+1), tets 6*nx*ny*nz.
  * Call with NULL arrays for sizes.  bc_style 0 = "analytical" (face y=y0: type 2 value 0

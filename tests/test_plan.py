@@ -292,3 +292,86 @@ def test_numpy_kuhn_mesher_matches_the_product_mesher():
     w = kuhn_block(2, 3, 2, 5.0, 7.0, 4.0, 0.0, cube_origin=(1, 2, 1), full=(5, 7, 4))
     assert np.array_equal(a["nodes"][w["node_gid"]], w["nodes"])
     assert np.array_equal(w["node_gid"][w["conn"]], a["conn"][w["elem_gid"]])
+
+
+@pytest.mark.parametrize("nranks,rank", [(1, 0), (2, 0), (2, 1), (3, 1)])
+def test_cell_layout_of_the_direct_assembly_reproduces_the_pull_gather(nranks, rank):
+    """Direct (push) assembly, fea_plan.cpp "cell layout": the element kernel writes every staged block into the cell
+    edest names (transposed when bit 31 is set), gather_cells_kernel adds a column's layers position by position
+    and writes each upper slot and its mirror.  Emulated here with the kernels' own index arithmetic and compared
+    bit for bit with the pull gather over scptr / scsrc: same contributions, same order, every real slot written
+    exactly once, padding untouched."""
+    mb = fg.mesh_block(3, 2, 3, bc_style=1, dy=0.01)
+    p = fg.Plan(mb["nodes"], mb["conn"], rank=rank, nranks=nranks)
+    rng = np.random.default_rng(5)
+    ne, ne_pad = p.n_elems, (p.n_elems + 31) // 32 * 32
+    staged = rng.standard_normal((ne, 55, 3, 3))
+    for a in range(10):                                    # K_e is symmetric: so are its diagonal blocks
+        c = TRI[(a, a)]
+        staged[:, c] = staged[:, c] + staged[:, c].transpose(0, 2, 1)
+    # pull gather in slot order, one add per contribution starting from zero (gather_item)
+    pull = np.zeros((p.n_slots, 3, 3))
+    for s in range(p.n_slots):
+        for k in range(p.scptr[s], p.scptr[s + 1]):
+            src = int(p.scsrc[k])
+            blk = staged[(src & 0x7fffffff) // 55, (src & 0x7fffffff) % 55]
+            pull[s] = pull[s] + (blk.T if src >> 31 else blk)
+    real = np.diff(p.scptr) > 0
+    # element kernel: cells
+    assert p.edest.shape == (55, ne_pad) and (p.edest[:, ne:] == 0xffffffff).all()
+    cells = np.full((p.n_cells, 10), np.nan)
+    written = np.zeros(p.n_cells, int)
+    for e in range(ne):
+        for code in range(55):
+            d = int(p.edest[code, e])
+            if d == 0xffffffff:
+                continue
+            blk = staged[e, code]
+            cells[d & 0x7fffffff, :9] = (blk.T if d >> 31 else blk).ravel()
+            written[d & 0x7fffffff] += 1
+    assert (written == 1).all()
+    # gather_cells_kernel
+    out = np.full((p.n_slots, 3, 3), np.nan)
+    hits = np.zeros(p.n_slots, int)
+    assert len(set(p.col_order.tolist())) == len(p.col_order) == p.n_cols_active
+    assert (np.diff(p.col_ready[p.col_order]) >= 0).all() and (p.col_ready[p.col_order] >= 0).all()
+    assert p.n_cols_active == int((p.col_ready >= 0).sum())
+    for col in p.col_order:
+        meta = p.cmeta[32 * col:32 * col + 32].astype(int)
+        n, rk = meta & 2047, meta >> 11
+        off = int(p.ccell[col])
+        acc = np.zeros((32, 9))
+        ready = -1
+        for k in range(n.max()):
+            m = int((n > k).sum())
+            acc[:m] = acc[:m] + cells[off:off + m, :9]
+            off += m
+        assert off == p.ccell[col + 1]
+        for lane in range(32):
+            if n[lane] == 0:
+                continue
+            slot = 32 * col + lane
+            v = acc[rk[lane]].reshape(3, 3)
+            out[slot] = v
+            hits[slot] += 1
+            mp = int(p.cmirror[slot])
+            if mp >= 0:
+                mcol, ml = divmod(mp, 288)
+                assert ml < 32
+                out[32 * mcol + ml] = v.T
+                hits[32 * mcol + ml] += 1
+        srcs = np.concatenate([p.scsrc[p.scptr[32 * col + l]:p.scptr[32 * col + l + 1]] for l in range(32) if n[l]])
+        assert p.col_ready[col] == int(((srcs & 0x7fffffff) // 55).max())
+    assert (hits[real] == 1).all() and (hits[~real] == 0).all()
+    assert np.array_equal(out[real], pull[real])
+    # upper slots are exactly the real slots with column >= row; ranks of a column are a permutation prefix
+    row_of_slot = np.full(p.n_slots, -1)
+    for s in range(p.n_slices):
+        base, width = p.slice_ptr[s], (p.slice_ptr[s + 1] - p.slice_ptr[s]) // 32
+        for l in range(32):
+            r = p.sell_row[32 * s + l]
+            if r >= 0:
+                row_of_slot[base + 32 * np.arange(width) + l] = r
+    upper = real & (p.sbcol >= row_of_slot)
+    assert np.array_equal((p.cmeta & 2047) > 0, upper)
+    assert np.array_equal((p.cmeta & 2047)[upper], np.diff(p.scptr)[upper])
