@@ -120,6 +120,8 @@ struct fea_gpu_ctx {
   struct AsmGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
   std::map<int, AsmGraph> asm_graphs;  // captured chunk sequences, one per (residual, Dirichlet, chunk size) variant
   cudaEvent_t ev_asm = nullptr;
+  int gather_pipe = 0;             // 0 = one contribution per trip; 5 / 6 / 8 = two per trip with that many CTAs of 128 threads per SM as the register cap
+  int gather_sym = 1;              // pull gather: 1 = sum the upper triangle only and store each block into its mirror slot too, 0 = every slot sums its own list
   int gather_mode = 1;             // 1 = lane per slot (gather_blocks_kernel, default), 9 = nine lanes per block (gather_blocks9_kernel: 41 % fewer L1 sectors, same time -- DESIGN 4)
   bool gather9_ok = false;         // the uploaded lists satisfy what gather_blocks9_kernel assumes
 
@@ -380,6 +382,8 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   if (const char *s = getenv("FEA_GATHER_SPLIT")) fea_gpu_set_param(c, "gather_split", atof(s));
   if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
   if (const char *s = getenv("FEA_CHUNK_TILES")) fea_gpu_set_param(c, "chunk_tiles", atof(s));
+  if (const char *s = getenv("FEA_GATHER_SYM")) fea_gpu_set_param(c, "gather_sym", atof(s));
+  if (const char *s = getenv("FEA_GATHER_PIPE")) fea_gpu_set_param(c, "gather_pipe", atof(s));
   if (const char *s = getenv("FEA_PCG_VARIANT")) fea_gpu_set_param(c, "pcg_variant", atof(s));
   if (const char *s = getenv("FEA_PCG_OVERLAP")) fea_gpu_set_param(c, "pcg_overlap", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
@@ -925,7 +929,7 @@ static int ensure_cells(fea_gpu_ctx *c) {
   const fea::Plan &pl = c->plan;
   TRY(dev_upload(&c->cmeta, pl.cmeta, c->stream));
   TRY(dev_upload(&c->ccell, pl.ccell, c->stream));
-  TRY(dev_upload(&c->cmirror, pl.cmirror, c->stream));
+  if (!c->cmirror) TRY(dev_upload(&c->cmirror, pl.cmirror, c->stream));
   TRY(dev_upload(&c->col_order, pl.col_order, c->stream));
   TRY(dev_upload(&c->edest, pl.edest, c->stream));
   c->n_cols_active = (int)pl.col_order.size();
@@ -1083,16 +1087,28 @@ static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
     return FEA_GPU_OK;
   }
   {
+    if (c->gather_sym && !c->cmirror) {
+      TRY(dev_upload(&c->cmirror, c->plan.cmirror, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    const int32_t *mir = c->gather_sym ? c->cmirror : nullptr;
     const int sp = c->gather_split;
     const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
     if (c->gather_mode == 9 && c->gather9_ok && !FEA_KE_INTERLEAVED)
       fea::gather_blocks9_kernel<4, FEA_G9_MINCTAS><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
     else
+    if (c->gather_pipe == 5)
+      fea::gather_blocks_kernel<128, 5, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
+    else if (c->gather_pipe == 6)
+      fea::gather_blocks_kernel<128, 6, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
+    else if (c->gather_pipe == 8)
+      fea::gather_blocks_kernel<128, 8, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
+    else
     switch (c->gather_threads) {
-      case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
-      case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
-      case 128: fea::gather_blocks_kernel<128, 8><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
-      default: fea::gather_blocks_kernel<256, 5><<<grid, 256, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf); break;
+      case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
+      case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
+      case 128: fea::gather_blocks_kernel<128, 8><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
+      default: fea::gather_blocks_kernel<256, 5><<<grid, 256, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
     }
   }
   LAUNCHED();
@@ -1718,10 +1734,6 @@ extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, dou
   }
   CHECK_H(c);
   if (!ke900 || element < 0 || element >= c->plan.n_elems_global) return FEA_GPU_ERR_ARG;
-  if (FEA_KE_INTERLEAVED) {
-    g_err = "fea_gpu_get_element_matrix: not available in the interleaved staging build";
-    return FEA_GPU_ERR_ARG;
-  }
   ensure_elem_map(c);
   const int32_t le = c->elem_g2l[(size_t)element];
   if (le < 0) {
@@ -1750,7 +1762,11 @@ extern "C" int fea_gpu_get_element_matrix(fea_gpu_handle c, int32_t element, dou
       g_err = "no stiffness assembled yet";
       return FEA_GPU_ERR_ARG;
     }
-    CU(cudaMemcpyAsync(st, c->Ke + (size_t)le * fea::KE_STRIDE, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    if (FEA_KE_INTERLEAVED)   // 16-byte chunk k of the element at double offset ((le / 32) 250 + k) 64 + 2 (le % 32)
+      CU(cudaMemcpy2DAsync(st, 16, c->Ke + (size_t)(le / 32) * (32 * fea::KE_STRIDE) + 2 * (le % 32), 512, 16, fea::KE_STRIDE / 2,
+                           cudaMemcpyDeviceToHost, c->stream));
+    else
+      CU(cudaMemcpyAsync(st, c->Ke + (size_t)le * fea::KE_STRIDE, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   for (int a = 0; a < fea::NEN; ++a)
@@ -1813,7 +1829,7 @@ extern "C" int fea_gpu_get_csr(fea_gpu_handle c, int64_t *n_rows, int64_t *nnz, 
       for (auto &pr : order)
         for (int j = 0; j < 3; ++j, ++out) {
           if (colidx) colidx[out] = 3 * pr.first + j;
-          if (vals) vals[out] = sv[(size_t)(9 * (sbase + (int64_t)pr.second * fea::SELL_C) + 32 * (3 * i + j) + lane)];
+          if (vals) vals[out] = sv[(size_t)(9 * (sbase + (int64_t)pr.second * fea::SELL_C) + fea::val_off(3 * i + j, lane))];
         }
     }
   }
@@ -2018,6 +2034,8 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   else if (k == "gather_mode" && (v == 1 || v == 9 || v == 2)) c->gather_mode = v;
   else if (k == "chunk_tiles" && v >= 0) c->chunk_tiles = v;
   else if (k == "cells_dbg" && v >= 0) c->cells_dbg = v;
+  else if (k == "gather_sym" && (v == 0 || v == 1)) c->gather_sym = v;
+  else if (k == "gather_pipe" && (v == 0 || v == 5 || v == 6 || v == 8)) c->gather_pipe = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else if (k == "pcg_variant" && v >= 0 && v <= 1) c->pcg_variant = v;

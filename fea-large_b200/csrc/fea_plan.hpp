@@ -25,8 +25,11 @@ constexpr int KE_STRIDE = 500;          // doubles per element
 // element-kernel CTA -- chunk c of element e at double offset ((e / 32) 250 + c) 64 + 2 (e % 32) -- so that
 // the element kernel stores straight from registers (a warp store = 512 contiguous bytes) instead of
 // transposing through shared memory; the gather then reads its five chunks at a 512-byte stride.
+// Default since round 2: with the upper-triangle gather (every staged block read once) the strided reads cost the
+// gather nothing (1.81 vs 1.84 ms) and the element kernel drops from 1.38 to 1.19 ms (profiles/r2_assembly_variants.md).
+// -DFEA_KE_INTERLEAVED=0 builds the flat layout (Makefile: variant-flat).
 #ifndef FEA_KE_INTERLEAVED
-#define FEA_KE_INTERLEAVED 0
+#define FEA_KE_INTERLEAVED 1
 #endif
 #if defined(__CUDACC__)
 #define FEA_HD __host__ __device__
@@ -51,6 +54,13 @@ constexpr int CELL_RANK_SHIFT = 11;     // high 5 bits: position of the slot ins
 constexpr uint32_t CELL_NONE = 0xffffffffu;
 
 constexpr int SELL_C = 32;              // rows per SELL slice = one warp
+// Value layout of a 32-slot SELL column (288 doubles at 288 * column): components c = 3 i + j of lane l sit at
+//   c 0-3: 4 l + c        c 4-7: 128 + 4 l + (c - 4)        c 8: 256 + l
+// i.e. every lane owns two whole 32-byte sectors per column plus one double: the SpMV reads a column with two
+// 256-bit loads and one 64-bit load per lane (1024 + 1024 + 256 contiguous bytes per warp), and a single slot can be
+// written from anywhere (the transposed store into the lower triangle) without touching a sector another lane
+// owns -- with one component per 256-byte row those stores were partial sectors (read-modify-write in DRAM).
+FEA_HD inline int val_off(int c, int lane) { return c < 8 ? ((c >> 2) << 7) + (lane << 2) + (c & 3) : 256 + lane; }
 constexpr int SELL_SIGMA = 2048;        // rows per length-sorting window
 
 struct Plan {
@@ -78,7 +88,7 @@ struct Plan {
   // SELL-32-sigma copy of the block pattern: what the device kernels use.  Rows are sorted by
   // length inside windows of SELL_SIGMA rows and cut into slices of 32; slot (row r = lane l of
   // slice s, j-th block of the row) = slice_ptr[s] + 32 j + l, its 9 values live at
-  // 9 (slice_ptr[s] + 32 j) + 32 c + l  (c = 3 i + j'): every warp load is 256 contiguous bytes.
+  // 9 (slice_ptr[s] + 32 j) + val_off(c, l)  (c = 3 i + j').
   int32_t n_slices = 0;
   std::vector<int32_t> sell_row;        // [n_slices*32] local row of each lane, -1 = padding lane
   std::vector<int32_t> row_lane;        // [n_own] slice*32 + lane of each row
@@ -86,7 +96,7 @@ struct Plan {
   std::vector<int32_t> sbcol;           // [n_slots] column node of each slot (padding: the row's own node)
   std::vector<int32_t> scptr;           // [n_slots+1] gather map in slot order
   std::vector<uint32_t> scsrc;          // [ncontrib]
-  std::vector<int32_t> sdiag;           // [n_own] value index of the (0,0) entry of the diagonal block
+  std::vector<int32_t> sdiag;           // [n_own] 9 * (first slot of the diagonal block's column) + lane
   int64_t n_slots() const { return (int64_t)sbcol.size(); }
 
   // direct (push) assembly, see "cell layout" in fea_plan.cpp

@@ -89,62 +89,123 @@ struct SellMat {
   double *vals;               // [n_slots * 9]
 };
 
+// 256-bit accesses to the value array (fea_plan.hpp: val_off): a lane's components 0-3 / 4-7 of one column
+__device__ __forceinline__ void ld_vals4(const double *p, double &a, double &b, double &c, double &d) {
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st_vals4(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// the nine values of lane `lane` in the column starting at `colv` (= vals + 288 * column)
+__device__ __forceinline__ void store_slot(double *colv, int lane, const double (&v)[9]) {
+  st_vals4(colv + 4 * lane, v[0], v[1], v[2], v[3]);
+  st_vals4(colv + 128 + 4 * lane, v[4], v[5], v[6], v[7]);
+  colv[256 + lane] = v[8];
+}
+// the same block transposed, into the slot whose value index (288 * column + lane) is `mp`
+__device__ __forceinline__ void store_slot_transposed(double *vals, int mp, const double (&v)[9]) {
+  const int ml = mp % 288;
+  double *colv = vals + (mp - ml);
+  st_vals4(colv + 4 * ml, v[0], v[3], v[6], v[1]);
+  st_vals4(colv + 128 + 4 * ml, v[4], v[7], v[2], v[5]);
+  colv[256 + ml] = v[8];
+}
+
 // K3: gather assembly.  Each lane owns one block slot and sums its contributions in the order
 // of the precomputed list (ascending global element id = the reference's element-major
 // accumulation, fea_solver.c:878-882), so results are bit-reproducible run to run and need
 // no atomics.  Optionally applies the Dirichlet cancellation in the same pass, from one flag byte
 // per slot (the prescribed DOFs are fixed when the context is created).
 // Work item = one slot column of one slice (32 slots, one warp).
+// With `cmirror` (value index of the mirror slot, -1 = none; fea_plan.cpp "cell layout") only the upper triangle
+// (column >= row) is summed: K_e is symmetric, the list of slot (J, I) is the list of (I, J) with every block
+// transposed, so its sum is bit for bit the transpose -- the lane stores it into the mirror slot instead of a
+// second lane gathering the same 72-byte blocks again.  Halves the L1 sector requests that bound this kernel.
+// one staged block: the aligned 80 bytes around it (five 16-byte loads)
+__device__ __forceinline__ void load_staged(const double *__restrict__ Ke, uint32_t src, double (&w)[10]) {
+  const uint32_t idx = src & 0x3fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp); bit 30: see SRC_LAST
+  // 72 bytes at an 8-byte boundary: five 16-byte loads of the enclosing aligned 80 bytes (the
+  // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones: the
+  // 32 lanes of a warp read 32 unrelated blocks, so every load costs 32 L1 sector requests.
+  // Three 32-byte LDG.256 of the enclosing 96 bytes were measured too: no faster, more data moved.
+#if FEA_KE_INTERLEAVED
+  const uint32_t el = idx / 55u, code = idx - 55u * el, rg = code / 11u;
+  const uint32_t o = 100u * rg + 9u * (code - 11u * rg);       // offset inside the element, doubles
+  const double2 *p = reinterpret_cast<const double2 *>(Ke) + ((size_t)(el >> 5) * 250 + (o >> 1)) * 32 + (el & 31u);
+#pragma unroll
+  for (int h = 0; h < 5; ++h) {
+    const double2 t = p[h * 32];
+    w[2 * h] = t.x;
+    w[2 * h + 1] = t.y;
+  }
+#else
+  const size_t off = (size_t)idx * 9 + idx / 11u;
+  const double2 *p = reinterpret_cast<const double2 *>(Ke + (off & ~(size_t)1));
+#pragma unroll
+  for (int h = 0; h < 5; ++h) {
+    const double2 t = p[h];
+    w[2 * h] = t.x;
+    w[2 * h + 1] = t.y;
+  }
+#endif
+}
+__device__ __forceinline__ void add_staged(uint32_t src, const double (&w)[10], double (&acc)[9]) {
+  const uint32_t idx = src & 0x3fffffffu;
+#if FEA_KE_INTERLEAVED
+  const uint32_t code = idx % 55u, rg = code / 11u;
+  const bool odd = ((100u * rg + 9u * (code - 11u * rg)) & 1u) != 0;
+#else
+  const bool odd = ((idx * 9u + idx / 11u) & 1u) != 0;     // parity survives the 32-bit wrap
+#endif
+  double v[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) v[c] = odd ? w[c + 1] : w[c];
+  if (src >> 31) {  // stored block is K_e[b][a]: add its transpose
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] += v[(c % 3) * 3 + c / 3];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] += v[c];
+  }
+}
+
+// PIPE: two contributions per trip, the list words of the next trip already in flight while this trip's blocks
+// load -- a slot's chain of dependent round trips (list word -> block, per contribution) is what the lanes wait
+// for (long-scoreboard stalls, 42 % of the warp slots occupied); same adds in the same order.
+template <bool PIPE>
 __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__restrict__ cptr,
                                             const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
-                                            const uint8_t *__restrict__ sflag, int s, int j, int lane) {
+                                            const uint8_t *__restrict__ sflag, const int32_t *__restrict__ cmirror,
+                                            int s, int j, int lane) {
   const int base = A.slice_ptr[s];
   const int slot = base + (j << 5) + lane;
   const int k0 = cptr[slot], k1 = cptr[slot + 1];
+  int mp = -1;
+  if (cmirror) {
+    if (k1 > k0 && A.bcol[slot] < A.sell_row[s * 32 + lane]) return;   // lower triangle: written by its mirror
+    mp = cmirror[slot];
+  }
   const unsigned f = sflag ? sflag[slot] : 0u;   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k = k0; k < k1; ++k) {
-    const uint32_t src = csrc[k];
-    const uint32_t idx = src & 0x3fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp); bit 30: see SRC_LAST
-    const size_t off = (size_t)idx * 9 + idx / 11u;
-    // 72 bytes at an 8-byte boundary: five 16-byte loads of the enclosing aligned 80 bytes (the
-    // extra double is the neighbouring block's or the region's pad) instead of nine 8-byte ones: the
-    // 32 lanes of a warp read 32 unrelated blocks, so every load costs 32 L1 sector requests and that
-    // request rate (~1 per clock and SM) is what bounds this kernel.  Three 32-byte LDG.256 of the
-    // enclosing 96 bytes were measured too: no faster (1.97 vs 2.00 ms at best), more data moved.
-#if FEA_KE_INTERLEAVED
-    const uint32_t el = idx / 55u, code = idx - 55u * el, rg = code / 11u;
-    const uint32_t o = 100u * rg + 9u * (code - 11u * rg);       // offset inside the element, doubles
-    const double2 *p = reinterpret_cast<const double2 *>(Ke) + ((size_t)(el >> 5) * 250 + (o >> 1)) * 32 + (el & 31u);
-    const bool odd = (o & 1u) != 0;
-    double w[10];
-#pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      const double2 t = p[h * 32];
-      w[2 * h] = t.x;
-      w[2 * h + 1] = t.y;
+  if (PIPE) {
+    uint32_t a = k0 < k1 ? csrc[k0] : 0u, b = k0 + 1 < k1 ? csrc[k0 + 1] : 0u;
+    for (int k = k0; k < k1; k += 2) {
+      const bool two = k + 1 < k1;
+      const uint32_t na = k + 2 < k1 ? csrc[k + 2] : 0u, nb = k + 3 < k1 ? csrc[k + 3] : 0u;
+      double w0[10], w1[10];
+      load_staged(Ke, a, w0);
+      if (two) load_staged(Ke, b, w1);
+      add_staged(a, w0, acc);
+      if (two) add_staged(b, w1, acc);
+      a = na;
+      b = nb;
     }
-    (void)off;
-#else
-    const double2 *p = reinterpret_cast<const double2 *>(Ke + (off & ~(size_t)1));
-    const bool odd = (off & 1) != 0;
-    double w[10];
-#pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      const double2 t = p[h];
-      w[2 * h] = t.x;
-      w[2 * h + 1] = t.y;
-    }
-#endif
-    double v[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) v[c] = odd ? w[c + 1] : w[c];
-    if (src >> 31) {  // stored block is K_e[b][a]: add its transpose
-#pragma unroll
-      for (int c = 0; c < 9; ++c) acc[c] += v[(c % 3) * 3 + c / 3];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 9; ++c) acc[c] += v[c];
+  } else {
+    for (int k = k0; k < k1; ++k) {
+      const uint32_t src = csrc[k];
+      double w[10];
+      load_staged(Ke, src, w);
+      add_staged(src, w, acc);
     }
   }
   if (f & 63u) {
@@ -154,9 +215,8 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
       if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) acc[c] = 0.0;
     }
   }
-  double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
-#pragma unroll
-  for (int c = 0; c < 9; ++c) out[c * 32] = acc[c];
+  store_slot(A.vals + (size_t)(base + (j << 5)) * 9, lane, acc);
+  if (mp >= 0) store_slot_transposed(A.vals, mp, acc);
 }
 
 // `split` consecutive CTAs per slice, their warps take the slot columns round-robin.  CTAs are
@@ -173,10 +233,11 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 // component) (coalesced 72-byte reads: 3.25 instead of 5 sector requests per block, but ~6x the
 // instructions per contribution and one row's diagonal list, up to 24 deep, serialises its warp)
 // were all slower (profiles/r1b_gather_variants.md).
-template <int THREADS, int MIN_CTAS>
+template <int THREADS, int MIN_CTAS, bool PIPE = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
-                           const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */) {
+                           const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */,
+                           const int32_t *__restrict__ cmirror /* null: every slot sums its own list */) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
   // `split` consecutive CTAs share a slice (columns dealt round-robin over their warps): the same
@@ -184,7 +245,7 @@ gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, con
   const int s = blockIdx.x / split, part = blockIdx.x - s * split;
   if (s >= A.n_slices) return;
   const int width = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
-  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, sflag, s, j, lane);
+  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item<PIPE>(A, cptr, csrc, Ke, sflag, cmirror, s, j, lane);
 }
 
 // K3, second mapping: NINE LANES PER BLOCK.  The lane-per-slot kernel above makes every 16-byte load of
@@ -278,14 +339,15 @@ gather_blocks9_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, co
     __syncwarp();
     // lane = slot from here: Dirichlet flags, then nine coalesced stores
     const unsigned f = sflag ? sflag[slot0 + lane] : 0u;   // per-slot flags, see gather_item
-    double *out = A.vals + (size_t)slot0 * 9 + lane;
+    double a9[9];
 #pragma unroll
     for (int c2 = 0; c2 < 9; ++c2) {
       double a = tile[lane * 9 + c2];
       const int i = c2 / 3, jj = c2 % 3;
       if ((f & 63u) && (((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) a = 0.0;
-      out[c2 * 32] = a;
+      a9[c2] = a;
     }
+    store_slot(A.vals + (size_t)slot0 * 9, lane, a9);
     __syncwarp();
   }
 }
@@ -368,17 +430,9 @@ gather_cells_kernel(int n_cols, const int32_t *__restrict__ col_order, const int
         if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) v[c] = 0.0;
       }
     }
-    double *out = vals + (size_t)col * (32 * 9) + lane;
-    if (!(dbg & 2)) {
-#pragma unroll
-      for (int c = 0; c < 9; ++c) out[c * 32] = v[c];
-    }
+    if (!(dbg & 2)) store_slot(vals + (size_t)col * (32 * 9), lane, v);
     const int mp = (dbg & 1) ? -1 : cmirror[slot];
-    if (mp >= 0) {
-      double *mo = vals + mp;
-#pragma unroll
-      for (int c = 0; c < 9; ++c) mo[c * 32] = v[(c % 3) * 3 + c / 3];
-    }
+    if (mp >= 0) store_slot_transposed(vals, mp, v);
   }
 }
 
@@ -412,17 +466,21 @@ cancel_kernel(SellMat A, const uint8_t *__restrict__ sflag) {
     for (int j = 0; j < width; ++j) {
       const unsigned f = sflag[base + (j << 5) + lane];   // per-slot flags, see gather_item
       if (!(f & 63u)) continue;
-      double *out = A.vals + (size_t)(base + (j << 5)) * 9 + lane;
+      double *out = A.vals + (size_t)(base + (j << 5)) * 9;
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         const int i = c / 3, jj = c % 3;
-        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) out[c * 32] = 0.0;
+        if ((((f >> i) | (f >> (3 + jj))) & 1u) && !((f & 64u) && i == jj)) out[val_off(c, lane)] = 0.0;
       }
     }
   }
 }
 
-// sdiag[row] = value index of the (0,0) entry of the row's diagonal block; (i,i) is 4 i * 32 further
+// sdiag[row] = 288 * column + lane of the row's diagonal block; its (i,i) entry is component 4 i (fea_plan.hpp: val_off)
+__device__ __forceinline__ size_t diag_index(int sd, int i) {
+  const int lane = sd % 288;
+  return (size_t)(sd - lane) + val_off(4 * i, lane);
+}
 __global__ void rhs_fix_kernel(int n, const double *__restrict__ vals, const int32_t *__restrict__ sdiag,
                                const uint8_t *__restrict__ pflag, const double *__restrict__ pval,
                                double lambda, double *__restrict__ R) {
@@ -430,7 +488,7 @@ __global__ void rhs_fix_kernel(int n, const double *__restrict__ vals, const int
   if (t >= n) return;
   if (pflag[t]) {
     const int row = t / 3, i = t - 3 * row;
-    R[t] = vals[(size_t)sdiag[row] + 128 * i] * (pval[t] * lambda);
+    R[t] = vals[diag_index(sdiag[row], i)] * (pval[t] * lambda);
   }
 }
 
@@ -439,7 +497,7 @@ __global__ void jacobi_kernel(int n, const double *__restrict__ vals, const int3
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int row = t / 3, i = t - 3 * row;
-  const double d = vals[(size_t)sdiag[row] + 128 * i];
+  const double d = vals[diag_index(sdiag[row], i)];
   dinv[t] = d != 0.0 ? 1.0 / d : 1.0;
 }
 
@@ -484,7 +542,7 @@ spmv_sell_kernel(int n_slices, const int32_t *__restrict__ slice_ptr, const int3
     const int base = slice_ptr[s];
     const int width = (slice_ptr[s + 1] - base) >> 5;
     const int row = sell_row[s * 32 + lane];
-    const double *v = vals + (size_t)base * 9 + lane;
+    const double *v = vals + (size_t)base * 9 + 4 * lane;
     const int32_t *bc = bcol + base + lane;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll 2
@@ -493,9 +551,13 @@ spmv_sell_kernel(int n_slices, const int32_t *__restrict__ slice_ptr, const int3
       const double *xc = x + 3 * (size_t)col;
       const double x0 = xc[0], x1 = xc[1], x2 = xc[2];
       const double *vj = v + (size_t)j * 288;
-      a0 = fma(vj[0], x0, fma(vj[32], x1, fma(vj[64], x2, a0)));
-      a1 = fma(vj[96], x0, fma(vj[128], x1, fma(vj[160], x2, a1)));
-      a2 = fma(vj[192], x0, fma(vj[224], x1, fma(vj[256], x2, a2)));
+      double k0, k1, k2, k3, k4, k5, k6, k7;
+      ld_vals4(vj, k0, k1, k2, k3);
+      ld_vals4(vj + 128, k4, k5, k6, k7);
+      const double k8 = __ldg(vj + 256 - 3 * lane);
+      a0 = fma(k0, x0, fma(k1, x1, fma(k2, x2, a0)));
+      a1 = fma(k3, x0, fma(k4, x1, fma(k5, x2, a1)));
+      a2 = fma(k6, x0, fma(k7, x1, fma(k8, x2, a2)));
     }
     if (row >= 0) {
       y[3 * (size_t)row] = a0;

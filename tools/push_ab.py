@@ -27,6 +27,14 @@ if what == "check":
     for model in (0, 1):
         g, mb = ctx(int(sys.argv[2]) if len(sys.argv) > 2 else 12, model)
         res = {}
+        g.set_param("gather_sym", 0)
+        g.assemble_all(True); ref0 = g.get_csr()[3].copy()
+        g.assemble_all(True, fuse_bc=True); ref1 = g.get_csr()[3].copy()
+        g.set_param("gather_sym", 1)
+        g.assemble_all(True); s0 = np.array_equal(ref0, g.get_csr()[3])
+        g.assemble_all(True, fuse_bc=True); s1 = np.array_equal(ref1, g.get_csr()[3])
+        print(f"model {model}: pull, upper triangle + mirror stores == every slot its own list: {s0} (plain) {s1} (Dirichlet)", flush=True)
+        ok &= s0 and s1
         for tag, mode, chunk, fuse in (("pull", 1, 0, False), ("push", 2, 0, False), ("push chunk 37", 2, 37, False),
                                        ("pull bc", 1, 0, True), ("push bc", 2, 0, True), ("push bc chunk 64", 2, 64, True),
                                        ("push bc chunk 1", 2, 1, True)):
@@ -79,7 +87,23 @@ def run(tag, reps=10):
           f"gather_r {p['gather_r']:.3f}  host-buffer step {e2e:.3f} ms", flush=True)
 
 
-g.set_param("gather_mode", 1); run("pull (mode 1)")
+g.set_param("gather_mode", 1)
+g.set_param("gather_sym", 0); run("pull, every slot its own list")
+g.set_param("gather_sym", 1); run("pull, upper + mirror (default)")
+for sp in [int(a) for a in os.environ.get("PULL_SPLITS", "").split(",") if a]:
+    g.set_param("gather_split", sp); run(f"pull, upper + mirror, split {sp}")
+g.set_param("gather_split", 8)
+for pp in [int(a) for a in os.environ.get("PULL_PIPES", "").split(",") if a]:
+    g.set_param("gather_pipe", pp); run(f"pull, upper + mirror, pipe {pp}")
+    if pp:
+        for sp in (4, 6):
+            g.set_param("gather_split", sp); run(f"pull, upper + mirror, pipe {pp}, split {sp}")
+        g.set_param("gather_split", 8)
+g.set_param("gather_pipe", 0)
+if os.environ.get("PUSH_SKIP"):
+    sys.exit(0)
+sp_ms = g.bench_spmv(20) if hasattr(g, "bench_spmv") else float("nan")
+print(f"spmv {sp_ms:.4f} ms", flush=True)
 g.set_param("gather_mode", 2)
 for dbg in [int(a) for a in os.environ.get("PUSH_DBG", "").split(",") if a]:
     g.set_param("cells_dbg", dbg)
