@@ -114,13 +114,15 @@ struct fea_gpu_ctx {
   int cells_dbg = 0;               // diagnostics (tools/push_ab.py): 1 no mirror stores, 2 no own stores, 4 no cell stores in the element kernel
   int chunk_tiles = 0;             // 0 = one element launch + one gather launch; > 0 = chunks of that many 32-element tiles
   std::vector<int32_t> chunk_cols; // [chunks + 1] prefix of col_order each chunk may gather
+  std::vector<int32_t> chunk_slices, slice_ready_sorted;   // the same for the pull gathers: prefix of slice_order
+  int32_t *slice_order = nullptr;  // slices by the last element any of their upper slots waits for
+  int chunk_overlap = 1;           // 1 = a chunk's gather runs on a second stream beside the next chunk's elements, 0 = one stream
   int chunk_cols_for = -1;         // chunk_tiles the list was built for
   cudaStream_t asm_stream = nullptr;   // the gathers of a chunked assembly run beside the next chunk's elements
   std::vector<cudaEvent_t> chunk_ev;
   struct AsmGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
   std::map<int, AsmGraph> asm_graphs;  // captured chunk sequences, one per (residual, Dirichlet, chunk size) variant
   cudaEvent_t ev_asm = nullptr;
-  int gather_pipe = 0;             // 0 = one contribution per trip; 5 / 6 / 8 = two per trip with that many CTAs of 128 threads per SM as the register cap
   int gather_sym = 1;              // pull gather: 1 = sum the upper triangle only and store each block into its mirror slot too, 0 = every slot sums its own list
   int gather_mode = 1;             // 1 = lane per slot (gather_blocks_kernel, default), 9 = nine lanes per block (gather_blocks9_kernel: 41 % fewer L1 sectors, same time -- DESIGN 4)
   bool gather9_ok = false;         // the uploaded lists satisfy what gather_blocks9_kernel assumes
@@ -383,7 +385,6 @@ static int create_impl(fea_gpu_ctx *c, int32_t n_nodes, int32_t n_elems, const d
   if (const char *s = getenv("FEA_GATHER_MODE")) fea_gpu_set_param(c, "gather_mode", atof(s));
   if (const char *s = getenv("FEA_CHUNK_TILES")) fea_gpu_set_param(c, "chunk_tiles", atof(s));
   if (const char *s = getenv("FEA_GATHER_SYM")) fea_gpu_set_param(c, "gather_sym", atof(s));
-  if (const char *s = getenv("FEA_GATHER_PIPE")) fea_gpu_set_param(c, "gather_pipe", atof(s));
   if (const char *s = getenv("FEA_PCG_VARIANT")) fea_gpu_set_param(c, "pcg_variant", atof(s));
   if (const char *s = getenv("FEA_PCG_OVERLAP")) fea_gpu_set_param(c, "pcg_overlap", atof(s));
   if (const char *s = getenv("FEA_PCG_BATCH")) {
@@ -718,7 +719,7 @@ extern "C" int fea_gpu_destroy(fea_gpu_handle c) {
                   c->p, c->q, c->r, c->dinv, c->u_saved, c->pflag, c->sflag, c->pval, c->inc_dof, c->inc_val,
                   c->send_nodes, c->send_buf, c->io_idx, c->own_idx, c->io_buf, c->partials, c->partials_b, c->counters, c->ctl, c->scalar, c->bad,
                   c->flush, c->export_buf, c->x_saved, c->ag_send, c->ag_recv, c->cz, c->cd, c->pd, c->sv, c->st2, c->sl_inner, c->sl_bound,
-                  c->cmeta, c->ccell, c->cmirror, c->col_order, c->edest, c->cells};
+                  c->cmeta, c->ccell, c->cmirror, c->col_order, c->edest, c->cells, c->slice_order};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -934,8 +935,6 @@ static int ensure_cells(fea_gpu_ctx *c) {
   TRY(dev_upload(&c->edest, pl.edest, c->stream));
   c->n_cols_active = (int)pl.col_order.size();
   TRY(dev_alloc(&c->cells, (size_t)std::max<int64_t>(pl.n_cells(), 1) * 5));
-  CU(cudaStreamCreateWithFlags(&c->asm_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming));
   CU(cudaStreamSynchronize(c->stream));
   return FEA_GPU_OK;
 }
@@ -947,6 +946,10 @@ static int ensure_ke(fea_gpu_ctx *c) {
 // prefix of col_order every chunk of `chunk_tiles` element tiles may gather: the columns whose last
 // contributing element lies before the end of the chunk
 static void build_chunks(fea_gpu_ctx *c) {
+  if (!c->asm_stream) {
+    cudaStreamCreateWithFlags(&c->asm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_asm, cudaEventDisableTiming);
+  }
   if (c->chunk_cols_for == c->chunk_tiles) return;
   const fea::Plan &pl = c->plan;
   const int n_tiles = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
@@ -957,6 +960,25 @@ static void build_chunks(fea_gpu_ctx *c) {
     const int64_t e_end = std::min<int64_t>((int64_t)(ch + 1) * c->chunk_tiles * fea::ELEMS_PER_CTA, c->n_elems);
     while (k < pl.col_order.size() && pl.col_ready[(size_t)pl.col_order[k]] < e_end) ++k;
     c->chunk_cols[(size_t)ch + 1] = (int32_t)k;
+  }
+  // pull gathers work slice by slice: a slice is ready when the last of its columns is
+  if (!c->slice_order) {
+    std::vector<int32_t> ready((size_t)pl.n_slices, -1), order((size_t)pl.n_slices);
+    for (int32_t sl = 0; sl < pl.n_slices; ++sl)
+      for (int32_t col = pl.slice_ptr[(size_t)sl] / fea::SELL_C; col < pl.slice_ptr[(size_t)sl + 1] / fea::SELL_C; ++col)
+        ready[(size_t)sl] = std::max(ready[(size_t)sl], pl.col_ready[(size_t)col]);
+    for (int32_t sl = 0; sl < pl.n_slices; ++sl) order[(size_t)sl] = sl;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ready[(size_t)a] < ready[(size_t)b]; });
+    c->slice_ready_sorted.resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) c->slice_ready_sorted[i] = ready[(size_t)order[i]];
+    if (dev_upload(&c->slice_order, order, c->stream) == FEA_GPU_OK) cudaStreamSynchronize(c->stream);
+  }
+  c->chunk_slices.assign((size_t)n_chunks + 1, 0);
+  k = 0;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int64_t e_end = ch + 1 == n_chunks ? INT64_MAX : (int64_t)(ch + 1) * c->chunk_tiles * fea::ELEMS_PER_CTA;
+    while (k < c->slice_ready_sorted.size() && c->slice_ready_sorted[k] < e_end) ++k;
+    c->chunk_slices[(size_t)ch + 1] = (int32_t)k;
   }
   while ((int)c->chunk_ev.size() < n_chunks) {
     cudaEvent_t ev;
@@ -976,6 +998,9 @@ static int launch_gather_cells(fea_gpu_ctx *c, int col0, int col1, bool with_bc,
 }
 
 static int element_launch(fea_gpu_ctx *c, bool with_k, bool with_r, fea::ElemArgs &a, int tile0, int n_tiles);
+static int launch_gather_pull(fea_gpu_ctx *c, bool with_bc, const int32_t *list, int n, cudaStream_t st);
+static int ensure_mirror(fea_gpu_ctx *c);
+static fea::SellMat sell_mat(fea_gpu_ctx *c);
 
 static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc = false, bool *gathered = nullptr) {
   fea::ElemArgs a;
@@ -1001,7 +1026,9 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc 
   CU(cudaMemsetAsync(c->bad, 0, sizeof(unsigned long long), c->stream));
   const int n_tiles = cdiv(c->n_elems, fea::ELEMS_PER_CTA);
   if (gathered) *gathered = false;
-  if (push && gathered && c->chunk_tiles > 0 && c->chunk_tiles < n_tiles) {
+  const bool pull_chunks = with_k && c->gather_mode == 1 && c->gather_sym;
+  if (pull_chunks) TRY(ensure_mirror(c));
+  if ((push || pull_chunks) && gathered && c->chunk_tiles > 0 && c->chunk_tiles < n_tiles) {
     // Chunked assembly: the element kernel runs chunk by chunk on the context's stream, and the columns that a
     // chunk completes are gathered on a second stream beside the next chunk's elements -- their cells were
     // written microseconds ago and are read back from L2 instead of HBM.
@@ -1009,7 +1036,8 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc 
     phase_begin(c, PH_ELEM);
     // The ~2 x chunks launches and their cross-stream dependencies are captured once per variant into a CUDA
     // graph: issued one by one from the host they cost more than the kernels take.
-    const int key = (with_r ? 1 : 0) | (chunk_bc ? 2 : 0) | (c->cells_dbg << 2) | (c->chunk_tiles << 8);
+    const int key = (with_r ? 1 : 0) | (chunk_bc ? 2 : 0) | ((c->cells_dbg & 7) << 2) | (push ? 32 : 0) | (c->chunk_overlap ? 64 : 0) |
+                    ((c->gather_split & 15) << 7) | (c->chunk_tiles << 11);
     auto it = c->asm_graphs.find(key);
     if (it == c->asm_graphs.end()) {
       const int n_chunks = (int)c->chunk_cols.size() - 1;
@@ -1023,9 +1051,17 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc 
         for (int ch = 0; ch < n_chunks; ++ch) {
           const int t0 = ch * c->chunk_tiles, nt = std::min(c->chunk_tiles, n_tiles - t0);
           TRY(element_launch(c, with_k, with_r, a, t0, nt));
-          CU(cudaEventRecord(c->chunk_ev[(size_t)ch], c->stream));
-          CU(cudaStreamWaitEvent(c->asm_stream, c->chunk_ev[(size_t)ch], 0));
-          TRY(launch_gather_cells(c, c->chunk_cols[(size_t)ch], c->chunk_cols[(size_t)ch + 1], chunk_bc, c->asm_stream));
+          cudaStream_t gs = c->stream;
+          if (c->chunk_overlap) {
+            CU(cudaEventRecord(c->chunk_ev[(size_t)ch], c->stream));
+            CU(cudaStreamWaitEvent(c->asm_stream, c->chunk_ev[(size_t)ch], 0));
+            gs = c->asm_stream;
+          }
+          if (push)
+            TRY(launch_gather_cells(c, c->chunk_cols[(size_t)ch], c->chunk_cols[(size_t)ch + 1], chunk_bc, gs));
+          else
+            TRY(launch_gather_pull(c, chunk_bc, c->slice_order + c->chunk_slices[(size_t)ch],
+                                   c->chunk_slices[(size_t)ch + 1] - c->chunk_slices[(size_t)ch], gs));
         }
         CU(cudaEventRecord(c->ev_asm, c->asm_stream));
         CU(cudaStreamWaitEvent(c->stream, c->ev_asm, 0));
@@ -1078,40 +1114,42 @@ static fea::SellMat sell_mat(fea_gpu_ctx *c) {
   return A;
 }
 
+// pull gather over all slices (list == nullptr) or over `n` entries of the device list `list`
+static int launch_gather_pull(fea_gpu_ctx *c, bool with_bc, const int32_t *list, int n, cudaStream_t st) {
+  if (n <= 0) return FEA_GPU_OK;
+  const uint8_t *pf = with_bc ? c->sflag : nullptr;
+  const int32_t *mir = c->gather_sym ? c->cmirror : nullptr;
+  const int sp = c->gather_split;
+  const int grid = n * sp;   // CTAs are dispatched in slice order
+  if (c->gather_mode == 9 && c->gather9_ok && !FEA_KE_INTERLEAVED && !list)
+    fea::gather_blocks9_kernel<4, FEA_G9_MINCTAS><<<grid, 128, 0, st>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
+  else
+    switch (c->gather_threads) {
+      case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, st>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir, list, n); break;
+      case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, st>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir, list, n); break;
+      case 128: fea::gather_blocks_kernel<128, 8><<<grid, 128, 0, st>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir, list, n); break;
+      default: fea::gather_blocks_kernel<256, 5><<<grid, 256, 0, st>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir, list, n); break;
+    }
+  LAUNCHED();
+  return FEA_GPU_OK;
+}
+
+static int ensure_mirror(fea_gpu_ctx *c) {
+  if (c->gather_sym && !c->cmirror) {
+    TRY(dev_upload(&c->cmirror, c->plan.cmirror, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return FEA_GPU_OK;
+}
+
 static int gather_stiffness(fea_gpu_ctx *c, bool with_bc) {
   phase_begin(c, PH_GATHER_K);
-  const uint8_t *pf = with_bc ? c->sflag : nullptr;
   if (c->gather_mode == 2) {
     TRY(launch_gather_cells(c, 0, c->n_cols_active, with_bc, c->stream));
-    phase_end(c, PH_GATHER_K);
-    return FEA_GPU_OK;
+  } else {
+    TRY(ensure_mirror(c));
+    TRY(launch_gather_pull(c, with_bc, nullptr, c->plan.n_slices, c->stream));
   }
-  {
-    if (c->gather_sym && !c->cmirror) {
-      TRY(dev_upload(&c->cmirror, c->plan.cmirror, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-    }
-    const int32_t *mir = c->gather_sym ? c->cmirror : nullptr;
-    const int sp = c->gather_split;
-    const int grid = c->plan.n_slices * sp;   // CTAs are dispatched in slice order
-    if (c->gather_mode == 9 && c->gather9_ok && !FEA_KE_INTERLEAVED)
-      fea::gather_blocks9_kernel<4, FEA_G9_MINCTAS><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf);
-    else
-    if (c->gather_pipe == 5)
-      fea::gather_blocks_kernel<128, 5, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
-    else if (c->gather_pipe == 6)
-      fea::gather_blocks_kernel<128, 6, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
-    else if (c->gather_pipe == 8)
-      fea::gather_blocks_kernel<128, 8, true><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir);
-    else
-    switch (c->gather_threads) {
-      case 1024: fea::gather_blocks_kernel<1024, 1><<<grid, 1024, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
-      case 512: fea::gather_blocks_kernel<512, 2><<<grid, 512, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
-      case 128: fea::gather_blocks_kernel<128, 8><<<grid, 128, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
-      default: fea::gather_blocks_kernel<256, 5><<<grid, 256, 0, c->stream>>>(sell_mat(c), sp, c->cptr, c->csrc, c->Ke, pf, mir); break;
-    }
-  }
-  LAUNCHED();
   phase_end(c, PH_GATHER_K);
   return FEA_GPU_OK;
 }
@@ -2035,7 +2073,7 @@ extern "C" int fea_gpu_set_param(fea_gpu_handle c, const char *name, double valu
   else if (k == "chunk_tiles" && v >= 0) c->chunk_tiles = v;
   else if (k == "cells_dbg" && v >= 0) c->cells_dbg = v;
   else if (k == "gather_sym" && (v == 0 || v == 1)) c->gather_sym = v;
-  else if (k == "gather_pipe" && (v == 0 || v == 5 || v == 6 || v == 8)) c->gather_pipe = v;
+  else if (k == "chunk_overlap" && (v == 0 || v == 1)) c->chunk_overlap = v;
   else if (k == "pcg_batch" && v >= 1 && v <= 4096) c->pcg_batch = v;
   else if (k == "pcg_stall" && v >= 0) c->pcg_stall = v;
   else if (k == "pcg_variant" && v >= 0 && v <= 1) c->pcg_variant = v;

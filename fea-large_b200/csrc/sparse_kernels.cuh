@@ -169,10 +169,8 @@ __device__ __forceinline__ void add_staged(uint32_t src, const double (&w)[10], 
   }
 }
 
-// PIPE: two contributions per trip, the list words of the next trip already in flight while this trip's blocks
-// load -- a slot's chain of dependent round trips (list word -> block, per contribution) is what the lanes wait
-// for (long-scoreboard stalls, 42 % of the warp slots occupied); same adds in the same order.
-template <bool PIPE>
+// (Two contributions per trip with the next list words prefetched -- fewer dependent round trips, 80-90 registers --
+// was measured slower: 2.02-2.16 against 1.84 ms; the kernel wants resident warps, profiles/r2_assembly_variants.md.)
 __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__restrict__ cptr,
                                             const uint32_t *__restrict__ csrc, const double *__restrict__ Ke,
                                             const uint8_t *__restrict__ sflag, const int32_t *__restrict__ cmirror,
@@ -187,20 +185,7 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
   }
   const unsigned f = sflag ? sflag[slot] : 0u;   // bits 0-2: row DOFs prescribed, 3-5: column DOFs, 6: diagonal block
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (PIPE) {
-    uint32_t a = k0 < k1 ? csrc[k0] : 0u, b = k0 + 1 < k1 ? csrc[k0 + 1] : 0u;
-    for (int k = k0; k < k1; k += 2) {
-      const bool two = k + 1 < k1;
-      const uint32_t na = k + 2 < k1 ? csrc[k + 2] : 0u, nb = k + 3 < k1 ? csrc[k + 3] : 0u;
-      double w0[10], w1[10];
-      load_staged(Ke, a, w0);
-      if (two) load_staged(Ke, b, w1);
-      add_staged(a, w0, acc);
-      if (two) add_staged(b, w1, acc);
-      a = na;
-      b = nb;
-    }
-  } else {
+  {
     for (int k = k0; k < k1; ++k) {
       const uint32_t src = csrc[k];
       double w[10];
@@ -233,19 +218,22 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 // component) (coalesced 72-byte reads: 3.25 instead of 5 sector requests per block, but ~6x the
 // instructions per contribution and one row's diagonal list, up to 24 deep, serialises its warp)
 // were all slower (profiles/r1b_gather_variants.md).
-template <int THREADS, int MIN_CTAS, bool PIPE = false>
+template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,
                            const double *__restrict__ Ke, const uint8_t *__restrict__ sflag /* may be null */,
-                           const int32_t *__restrict__ cmirror /* null: every slot sums its own list */) {
+                           const int32_t *__restrict__ cmirror /* null: every slot sums its own list */,
+                           const int32_t *__restrict__ slice_list /* null: all slices, else n_list of them (chunked assembly) */,
+                           int n_list) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
   // `split` consecutive CTAs share a slice (columns dealt round-robin over their warps): the same
   // number of resident warps then covers `split` times fewer slices, i.e. a smaller L2 footprint
-  const int s = blockIdx.x / split, part = blockIdx.x - s * split;
-  if (s >= A.n_slices) return;
+  const int si = blockIdx.x / split, part = blockIdx.x - si * split;
+  if (si >= n_list) return;
+  const int s = slice_list ? slice_list[si] : si;
   const int width = (A.slice_ptr[s + 1] - A.slice_ptr[s]) >> 5;
-  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item<PIPE>(A, cptr, csrc, Ke, sflag, cmirror, s, j, lane);
+  for (int j = part * nwarps + warp; j < width; j += nwarps * split) gather_item(A, cptr, csrc, Ke, sflag, cmirror, s, j, lane);
 }
 
 // K3, second mapping: NINE LANES PER BLOCK.  The lane-per-slot kernel above makes every 16-byte load of

@@ -12,10 +12,24 @@ from test_gpu_parity import RTOL_ELEM, RTOL_SOLVE, deformed, make_gpu, relmax
 pytestmark = pytest.mark.gpu
 
 
+GATHER_VARIANTS = {
+    # name: (gather_mode, gather_sym, chunk_tiles, chunk_overlap)
+    "every slot its own list": (1, 0, 0, 1),
+    "upper triangle + mirror (default)": (1, 1, 0, 1),
+    "nine lanes per block": (9, 0, 0, 1),
+    "upper + mirror, chunks of 3 tiles": (1, 1, 3, 0),
+    "upper + mirror, chunks of 7 tiles, gather beside the next chunk": (1, 1, 7, 1),
+    "direct (push) assembly": (2, 1, 0, 1),
+    "direct assembly, chunks of 5 tiles": (2, 1, 5, 1),
+}
+
+
 @pytest.mark.parametrize("case", ["neohook_brick", "kuhn6", "brick_fine"])
 def test_gather_modes_agree_bitwise(case):
-    """Both gathers sum every slot's list in the same order: identical bits, with and without the
-    Dirichlet cancellation folded in (fea_solver.c:873-883, :1244-1257)."""
+    """Every assembly variant sums a slot's contributions in the same order (ascending element id,
+    fea_solver.c:873-883): identical bits in K, with and without the Dirichlet cancellation folded in
+    (:1244-1257), whether a lane gathers every slot itself, only the upper triangle (the block goes to the mirror
+    slot transposed), the element kernel writes destination-ordered cells, or the work is cut into chunks."""
     if case == "kuhn6":
         m = block_model((6, 7, 5), model=0, bc_style=1, dy=0.01)
         x = deformed(m, 4, 0.004)
@@ -24,20 +38,26 @@ def test_gather_modes_agree_bitwise(case):
     else:
         m, _ = load_golden(case)
         x = deformed(m, 5)
+    g = make_gpu(m)
+    g.set_nodes(x)
     vals = {}
-    for mode in (1, 9):
-        g = make_gpu(m)
-        assert g.counts()["gather9"] == 1                      # the nine-lane kernel is what mode 9 runs here
-        g.set_param("gather_mode", mode)
-        g.set_nodes(x)
+    for name, (mode, sym, chunk, overlap) in GATHER_VARIANTS.items():
+        for k, v in (("gather_mode", mode), ("gather_sym", sym), ("chunk_tiles", chunk), ("chunk_overlap", overlap)):
+            g.set_param(k, v)
         g.assemble_all(True)
         plain = g.get_csr()[3].copy()
+        ke = g.element_matrix(len(m.conn) // 2)
         g.assemble_all(True, fuse_bc=True)
-        vals[mode] = (plain, g.get_csr()[3].copy())
-        g.close()
-    assert np.array_equal(vals[1][0], vals[9][0])
-    assert np.array_equal(vals[1][1], vals[9][1])
-    assert not np.array_equal(vals[9][0], vals[9][1])        # the cancellation did something
+        fused = g.get_csr()[3].copy()
+        g.assemble_stiffness()
+        vals[name] = (plain, fused, g.get_csr()[3].copy(), ke)
+    g.close()
+    ref = vals["every slot its own list"]
+    for name, v in vals.items():
+        for a, b in zip(ref, v):
+            assert np.array_equal(a, b), name
+    assert np.array_equal(ref[0], ref[2])
+    assert not np.array_equal(ref[0], ref[1])        # the cancellation did something
 
 
 @pytest.mark.parametrize("x0", [fg.X0_ZERO, fg.X0_RHS])

@@ -35,6 +35,14 @@ if what == "check":
         g.assemble_all(True, fuse_bc=True); s1 = np.array_equal(ref1, g.get_csr()[3])
         print(f"model {model}: pull, upper triangle + mirror stores == every slot its own list: {s0} (plain) {s1} (Dirichlet)", flush=True)
         ok &= s0 and s1
+        for ch, ov in ((37, 1), (64, 0), (5, 1)):
+            g.set_param("chunk_tiles", ch); g.set_param("chunk_overlap", ov)
+            g.assemble_all(True); s0 = np.array_equal(ref0, g.get_csr()[3])
+            g.assemble_all(True, fuse_bc=True); s1 = np.array_equal(ref1, g.get_csr()[3])
+            g.assemble_stiffness(); s2 = np.array_equal(ref0, g.get_csr()[3])
+            print(f"model {model}: pull in chunks of {ch} tiles (overlap {ov}) == unchunked: {s0} {s1} {s2}", flush=True)
+            ok &= s0 and s1 and s2
+        g.set_param("chunk_tiles", 0); g.set_param("chunk_overlap", 1)
         for tag, mode, chunk, fuse in (("pull", 1, 0, False), ("push", 2, 0, False), ("push chunk 37", 2, 37, False),
                                        ("pull bc", 1, 0, True), ("push bc", 2, 0, True), ("push bc chunk 64", 2, 64, True),
                                        ("push bc chunk 1", 2, 1, True)):
@@ -93,13 +101,11 @@ g.set_param("gather_sym", 1); run("pull, upper + mirror (default)")
 for sp in [int(a) for a in os.environ.get("PULL_SPLITS", "").split(",") if a]:
     g.set_param("gather_split", sp); run(f"pull, upper + mirror, split {sp}")
 g.set_param("gather_split", 8)
-for pp in [int(a) for a in os.environ.get("PULL_PIPES", "").split(",") if a]:
-    g.set_param("gather_pipe", pp); run(f"pull, upper + mirror, pipe {pp}")
-    if pp:
-        for sp in (4, 6):
-            g.set_param("gather_split", sp); run(f"pull, upper + mirror, pipe {pp}, split {sp}")
-        g.set_param("gather_split", 8)
-g.set_param("gather_pipe", 0)
+for spec in [a for a in os.environ.get("PULL_CHUNKS", "").split(",") if a]:     # tiles:overlap[:split]
+    f = [int(v) for v in spec.split(":")]
+    g.set_param("chunk_tiles", f[0]); g.set_param("chunk_overlap", f[1]); g.set_param("gather_split", f[2] if len(f) > 2 else 8)
+    run(f"pull, chunks of {f[0]} tiles, overlap {f[1]}, split {f[2] if len(f) > 2 else 8}")
+g.set_param("chunk_tiles", 0); g.set_param("gather_split", 8); g.set_param("chunk_overlap", 1)
 if os.environ.get("PUSH_SKIP"):
     sys.exit(0)
 sp_ms = g.bench_spmv(20) if hasattr(g, "bench_spmv") else float("nan")
