@@ -585,10 +585,13 @@ def main():
     asm_ms = elem_ms + gather_ms + gres_ms
     ach = BYTES_PER_ELEM * cnt["local_elems"] / (asm_ms * 1e-3) / 1e9
     tr = [traffic.get(k) for k in ("element_kernel", "gather_blocks_kernel", "gather_residual_kernel")]
-    roofline = {"bound": "hbm", "kernel": "assembly = element_kernel + gather_blocks9_kernel + gather_residual_kernel",
+    tr_sum = sum(tr) if all(v is not None for v in tr) else None
+    roofline = {"bound": "hbm", "kernel": "assembly = element_kernel + gather_blocks_kernel + gather_residual_kernel",
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": sum(tr) if all(v is not None for v in tr) else None,
-                "traffic_unit": "bytes per step (ncu dram read+write of the three kernels)",
+                "traffic": tr_sum,
+                "traffic_unit": "bytes per step (ncu dram read+write of the three kernels, profiles/ncu_traffic.json, quoted only while its source hash matches the kernels that ran)",
+                # how busy the memory system is with the bytes the kernels REALLY move (K_e staging included)
+                "dram_frac_on_measured_traffic": (tr_sum / (asm_ms * 1e-3) / 1e9 / hbm_peak) if tr_sum else None,
                 "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
                 "algorithmic_bytes_per_element": BYTES_PER_ELEM, "kernel_ms": asm_ms,
                 "kernel_ms_samples": ph.get("phase_samples"),

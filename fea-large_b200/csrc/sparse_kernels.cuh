@@ -120,7 +120,9 @@ __device__ __forceinline__ void store_slot_transposed(double *vals, int mp, cons
 // With `cmirror` (value index of the mirror slot, -1 = none; fea_plan.cpp "cell layout") only the upper triangle
 // (column >= row) is summed: K_e is symmetric, the list of slot (J, I) is the list of (I, J) with every block
 // transposed, so its sum is bit for bit the transpose -- the lane stores it into the mirror slot instead of a
-// second lane gathering the same 72-byte blocks again.  Halves the L1 sector requests that bound this kernel.
+// second lane gathering the same 72-byte blocks again.  Every staged block is then read exactly once; with that the
+// kernel moves 5.7 + 2.8 GB of DRAM traffic in 1.79 ms on C3 (4.8 TB/s, 73 % of the measured copy peak:
+// profiles/r2s_ncu_full_summary.md) -- it is HBM-bound on the K_e staging it has to read.
 // one staged block: the aligned 80 bytes around it (five 16-byte loads)
 __device__ __forceinline__ void load_staged(const double *__restrict__ Ke, uint32_t src, double (&w)[10]) {
   const uint32_t idx = src & 0x3fffffffu;       // 55 e + code -> 500 e + 100 pr + 9 pos (fea_plan.hpp); bit 30: see SRC_LAST
@@ -217,7 +219,8 @@ __device__ __forceinline__ void gather_item(const SellMat &A, const int32_t *__r
 // row is lost and the warps drift apart, 16 GB) and two warp-per-row mappings with lanes over (column,
 // component) (coalesced 72-byte reads: 3.25 instead of 5 sector requests per block, but ~6x the
 // instructions per contribution and one row's diagonal list, up to 24 deep, serialises its warp)
-// were all slower (profiles/r1b_gather_variants.md).
+// were all slower (profiles/r1b_gather_variants.md).  Round 2 (profiles/r2_assembly_variants.md): the slices can also be
+// taken from a list (`slice_list`), which is how the chunked assembly gathers what a chunk of elements completed.
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 gather_blocks_kernel(SellMat A, int split, const int32_t *__restrict__ cptr, const uint32_t *__restrict__ csrc,

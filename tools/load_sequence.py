@@ -2,6 +2,9 @@
 
     python -m torch.distributed.run --nproc-per-node N ... tools/load_sequence.py <n> <increments> [model] [bc_style]
     env: SEQ_DY (increment, default 0.2 = 20 % of a cell), SEQ_LIN_TOL (PCG tolerance, default 1e-12),
+         SEQ_TOTAL (total top-face displacement: <increments> is then ignored and the schedule is SEQ_DY0 (default
+         0.2), doubling every increment up to SEQ_DY, until the total is reached -- needs SEQ_PREDICTOR=1, which
+         scales its extrapolation by the ratio of consecutive increments), SEQ_PRECOND=1 (Chebyshev-Jacobi PCG),
          SEQ_PREDICTOR=1 (start every increment from x + (x - x_previous_increment): the boundary nodes move
          by the same increment every time, so this is the reference's boundary move plus a secant guess for the
          interior; the equilibrium Newton converges to is the same, it just starts closer),
@@ -54,7 +57,21 @@ g = fg.FeaGpu(mb["nodes"], mb["conn"], model, 100.0, 100.0, 5, mb["presc_node"],
 cnt = g.counts()
 if rank == 0:
     print(f"setup {time.time() - t0:.1f}s: {len(mb['conn'])} tets, {3 * len(mb['nodes'])} DOF, {world} rank(s), rank0 {cnt}", flush=True)
+if os.environ.get("SEQ_PRECOND", "0") == "1":
+    g.set_param("precond", 1)
+TOTAL = float(os.environ.get("SEQ_TOTAL", "0"))
+if TOTAL > 0:      # ramped schedule: the first (plain boundary move) increments stay small, later ones ride on the predictor
+    sizes, s = [], float(os.environ.get("SEQ_DY0", "0.2"))
+    while sum(sizes) < TOTAL - 1e-12:
+        sizes.append(min(s, DY, TOTAL - sum(sizes)))
+        s *= 2.0
+    increments = len(sizes)
+else:
+    sizes = [DY] * increments
+if rank == 0:
+    print(f"schedule: {increments} increments, sizes {sizes[:6]} ... {sizes[-2:]}, total {sum(sizes):.4f} (stretch {1 + sum(sizes) / L:.4f})", flush=True)
 log = []
+done_disp = 0.0
 sample = np.arange(0, len(mb["conn"]), 53, dtype=np.int32)    # elements whose sigma_yy is checked (every rank: the ones it holds)
 t_all = time.time()
 
@@ -68,14 +85,17 @@ def anybad():
 
 for step in range(1, increments + 1):
     g.sync(); ts = time.time()
+    size = sizes[step - 1]
     if PREDICTOR and step > 1:
-        g.extrapolate_nodes(1.0)                 # x <- 2 x_k - x_{k-1} (boundary nodes: exactly one more increment), saved <- x_k
+        # x <- x_k + (s_k / s_{k-1}) (x_k - x_{k-1}): the boundary nodes move by exactly this increment, saved <- x_k
+        g.extrapolate_nodes(size / sizes[step - 2])
         g.update_state()
         if anybad():                             # fall back to the plain boundary move
-            g.restore_nodes(); g.apply_increment(1.0)
+            g.restore_nodes(); g.save_nodes(); g.apply_increment(size / DY)
     else:
         g.save_nodes()
-        g.apply_increment(1.0)
+        g.apply_increment(size / DY)
+    done_disp += size
     its, pcg = 0, []
     while True:
         its += 1
@@ -93,7 +113,7 @@ for step in range(1, increments + 1):
         if rank == 0:
             print(json.dumps(dict(step=step, newton_iters=its, pcg_iters=pcg, last_R_dot_u=tol, seconds=dt)), flush=True)
         continue
-    k1 = 1.0 + step * DY / L
+    k1 = 1.0 + done_disp / L
     k2, sig = closed_form(k1)
     F, S, found = g.get_state_elems(sample)    # every rank checks the sampled elements it holds
     err = float(np.abs(S[found][:, :, 1, 1] / sig - 1).max()) if found.any() else 0.0
@@ -105,10 +125,14 @@ for step in range(1, increments + 1):
     log.append(rec)
     if rank == 0:
         print(json.dumps(rec), flush=True)
+    if bad > 0 or its >= 12 or not np.isfinite(tol):      # same on every rank (bad is all-reduced, tol is a global dot product)
+        if rank == 0:
+            print("ABORT: the sequence left the convergent path", flush=True)
+        break
 if rank == 0:
     print("SUMMARY", json.dumps(dict(n=n, tets=len(mb["conn"]), dof=3 * len(mb["nodes"]), ranks=world, model=model, dy=DY, lin_tol=LIN_TOL,
-                                     predictor=PREDICTOR, total_seconds=time.time() - t_all, final_stretch=1.0 + increments * DY / L,
+                                     predictor=PREDICTOR, total_seconds=time.time() - t_all, final_stretch=1.0 + done_disp / L, increments=increments, newton_total=sum(r['newton_iters'] for r in log) if CHECK_EVERY == 1 else None,
                                      worst_sigma_yy_rel_err=max(r["sigma_yy_max_rel_err"] for r in log),
-                                     newton_iters_total=None, steps=log)), flush=True)
+                                     steps=log)), flush=True)
 if dist is not None:
     dist.barrier(); dist.destroy_process_group()

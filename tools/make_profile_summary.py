@@ -1,12 +1,24 @@
 """Turn one evidence run's ncu outputs (gpurun_out/) into the tracked summaries under profiles/ (tools only).
 usage: make_profile_summary.py TAG   (reads gpurun_out/raw_TAG.csv from `ncu -i prof_TAG.ncu-rep --page raw --csv`
 and gpurun_out/TAG_launches.csv; writes profiles/TAG_ncu_full_summary.md, TAG_launches_summary.md, ncu_traffic.json)"""
-import collections, csv, json, os, sys
+import collections, csv, hashlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def kernel_source_hash():   # bench.py quotes ncu_traffic.json only while this still matches the sources it runs
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "fea-large_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+
 tag = sys.argv[1]
 NOTES = {
-    "element_kernel": "shared-memory pipe is the busy unit (column side streams 24 B per block and Gauss point, store tile 2x16 B per value); 10 warps/SM",
-    "gather_blocks_kernel [plain]": "8 CTAs of 128 threads per slice: ~185 slices in flight, their staging stays in L2; bound by L1 sector requests (every lane reads its own 72-byte block)",
+    "element_kernel": "interleaved staging, stores straight from registers; DRAM writes at ~4.4 TB/s are now the busy unit (K_e staging 4.0 GB + F, sigma 0.72 GB + R_e 0.24 GB); 10 warps/SM",
+    "gather_blocks_kernel [plain]": "upper triangle only + transposed store into the mirror slot: every staged block is read once; DRAM (read + write ~4.8 TB/s) and L2 are the busy units",
     "gather_blocks_kernel [Dirichlet flags folded in]": "what a bench step runs",
     "spmv_sell_kernel": "algorithmic 2.96 GB",
 }
@@ -57,9 +69,10 @@ for key, r in picked.items():
     md += [f"- {m}: {val(r, m)} {units[hdr.index(m)]}" for m in WANT if m in hdr]
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(md) + "\n")
 json.dump({"source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, one launch each, C3 = Kuhn 55^3 on one B200)",
-           "workload": {"n": 55, "n_gpus": 1},
+           "workload": {"n": 55, "n_gpus": 1}, "csrc_sha1": kernel_source_hash(),
            "dram_bytes_per_launch": {"element_kernel": traffic["element_kernel"],
                                      "gather_blocks_kernel": traffic["gather_blocks_kernel [Dirichlet flags folded in]"],
+                                     "gather_residual_kernel": traffic.get("gather_residual_kernel"),
                                      "spmv_sell_kernel": traffic["spmv_sell_kernel"]}},
           open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 
