@@ -162,6 +162,13 @@ void solve(fea_task_ptr task, fea_solution_params_ptr fea_params, nodes_array_pt
   /* FEA_KEEP_STEPS=0: no host snapshot per increment (9.5 GB each at 50 M DOF); only the last state is pulled
    * for the exporter.  Default: every increment, as the reference (fea_solver.c:233, :605-636). */
   const BOOL keep_steps = !(keep && atoi(keep) == 0);
+  /* FEA_PREDICTOR=1: from the second increment on, start from x_k + (x_k - x_{k-1}) instead of moving the boundary
+   * nodes alone (:168).  The prescribed nodes still move by exactly one increment (they moved by one in the previous
+   * one), the interior gets a secant guess: the same equilibrium in ~2 instead of ~5 Newton iterations
+   * (profiles/r2_large_runs.md).  Off by default: the reference's iterates are the default. */
+  const char *pred = getenv("FEA_PREDICTOR");
+  const BOOL predictor = pred && atoi(pred) == 1 && task->linesearch_max == 0;
+  BOOL prev_whole = FALSE;       /* the previous increment went in one part: the saved nodes are its start */
   LOG("Create elements database");
   solver_create_element_database(solver);
   LOG("Create an array of shape functions gradients in initial configuration");
@@ -177,14 +184,27 @@ void solve(fea_task_ptr task, fea_solution_params_ptr fea_params, nodes_array_pt
     BOOL failed = FALSE;
     while (remaining > 0.0 && !failed) {
       int64_t bad = 0;
+      BOOL predicted = FALSE;
       if (part > remaining) part = remaining;
-      gpu_must(fea_gpu_save_nodes(solver->gpu), "fea_gpu_save_nodes");
       it = 0;
-      solver_update_nodes_with_bc(solver, part);                 /* full value every increment, :168 */
+      if (predictor && prev_whole && part == 1.0) {
+        gpu_must(fea_gpu_extrapolate_nodes(solver->gpu, 1.0), "fea_gpu_extrapolate_nodes");   /* saved <- x_k */
+        predicted = TRUE;
+      } else {
+        gpu_must(fea_gpu_save_nodes(solver->gpu), "fea_gpu_save_nodes");
+        solver_update_nodes_with_bc(solver, part);               /* full value every increment, :168 */
+      }
       /* :171-179: gradients, stresses, K, keep K for modified Newton; the residual of the first
        * iteration (:185) comes out of the same element pass */
       gpu_must(fea_gpu_assemble_all(solver->gpu, 1), "fea_gpu_assemble_all");
       gpu_must(fea_gpu_bad_points(solver->gpu, &bad), "fea_gpu_bad_points");
+      if (bad > 0 && predicted) {                                /* the guess folded elements: plain boundary move */
+        LOGERROR("Load increment %d: %ld Gauss points inverted by the predictor, moving the boundary alone",
+                 solver->current_load_step + 1, (long)bad);
+        gpu_must(fea_gpu_restore_nodes(solver->gpu), "fea_gpu_restore_nodes");
+        prev_whole = FALSE;
+        continue;
+      }
       if (bad > 0 && part > 1.0 / 64.0) {
         LOGERROR("Load increment %d: %ld Gauss points inverted by a load fraction of %g, halving it",
                  solver->current_load_step + 1, (long)bad, part);
@@ -217,6 +237,7 @@ void solve(fea_task_ptr task, fea_solution_params_ptr fea_params, nodes_array_pt
           gpu_must(fea_gpu_update_nodes_scaled(solver->gpu, eta), "fea_gpu_update_nodes_scaled");
       } while (fabs(tolerance) > task->desired_tolerance && it < task->max_newton_count);
       if (it == task->max_newton_count) failed = TRUE;           /* the reference's test is on the count alone, :225 */
+      prev_whole = part == 1.0;
       remaining -= part;
       if (remaining > 0.0 && !failed)
         LOG("Load increment %d: fraction %g done, %g to go", solver->current_load_step + 1, part, remaining);

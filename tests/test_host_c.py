@@ -255,3 +255,24 @@ def test_feasolver_without_per_increment_snapshots(host, tmp_path):
     assert set(a) == {(k, s) for k in ("$NodeData", "$ElementData") for s in (0, 1, 2)}
     assert set(b) == {(k, s) for k in ("$NodeData", "$ElementData") for s in (0, 2)}
     assert np.array_equal(a[("$NodeData", 2)], b[("$NodeData", 2)])
+
+
+@pytest.mark.gpu
+def test_feasolver_secant_predictor_reaches_the_same_equilibria(host, tmp_path):
+    """FEA_PREDICTOR=1: increments after the first start from x_k + (x_k - x_{k-1}) (fea_gpu_extrapolate_nodes) instead
+    of the boundary move alone (fea_solver.c:168).  Same exported states, fewer Newton iterations."""
+    m = block_model((3, 4, 3), model=1, bc_style=2, dy=0.1)
+    m.desired_tolerance, m.max_newton, m.solver_type, m.modified_newton = 1e-12, 60, 0, False
+    path = str(tmp_path / "pred.sexp")
+    write_sexp(path, m, load_increments=5)
+    out, newton = {}, {}
+    for p in ("0", "1"):
+        run = subprocess.run([BIN, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=600,
+                             env=dict(os.environ, FEA_PREDICTOR=p))
+        assert run.returncode == 0, run.stderr[-2000:]
+        assert "Unable to finish" not in run.stdout and "inverted" not in run.stdout
+        out[p] = _msh_sections(str(tmp_path / "pred.msh"))
+        newton[p] = run.stdout.count("Newton iteration")
+    for key in out["0"]:
+        assert np.abs(out["0"][key] - out["1"][key]).max() <= 3e-6, key      # %f carries six decimals
+    assert newton["1"] < newton["0"], newton
