@@ -231,7 +231,14 @@ int fea_gpu_measure_dmma(int32_t device, double *dmma_tflops);
  * the context's stream): the halo exchange of one [local nodes][3] vector and the all-reduce of the
  * four iteration sums.  0 when nranks == 1.  Either pointer may be NULL.  Collective. */
 int fea_gpu_bench_comm(fea_gpu_handle h, int32_t reps, double *halo_ms, double *allreduce_ms);
-/* tuning knobs: "gather_mode" (9 = nine lanes per block, the default; 1 = one lane per block),
+/* tuning knobs (INTEGRATION.md has the table with the measurements behind every default):
+ * "gather_mode" (1 = pull gather, one lane per block slot, the default; 9 = nine lanes per staged block, flat-staging
+ * builds only; 2 = direct assembly: the element kernel writes destination-ordered cells, gather_cells_kernel adds
+ * them with coalesced loads), "gather_sym" (1 = the pull gather sums the upper block triangle only and stores every
+ * block into its mirror slot too, the default; 0 = every slot sums its own list), "chunk_tiles" (> 0: assembly in
+ * chunks of that many 32-element tiles captured into one CUDA graph, staging read back from L2; default 0),
+ * "chunk_overlap" (chunked assembly: gather beside the next chunk's elements; default 1), "gather_threads",
+ * "gather_split", "elem_ratio" -- all bitwise neutral for K;
  * "pcg_variant" (0 = classic two-reduction PCG, the default; 1 = single-reduction),
  * "pcg_overlap" (1 = halo exchange beside the interior SpMV slices; default 0),
  * "precond" (0 = Jacobi, the default; 1 = Chebyshev-accelerated Jacobi z = p_d(D^-1 A) D^-1 r -- what the
