@@ -121,7 +121,7 @@ struct fea_gpu_ctx {
   cudaStream_t asm_stream = nullptr;   // the gathers of a chunked assembly run beside the next chunk's elements
   std::vector<cudaEvent_t> chunk_ev;
   struct AsmGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
-  std::map<int, AsmGraph> asm_graphs;  // captured chunk sequences, one per (residual, Dirichlet, chunk size) variant
+  std::map<int64_t, AsmGraph> asm_graphs;  // captured chunk sequences, one per (residual, Dirichlet, chunk size) variant
   cudaEvent_t ev_asm = nullptr;
   int gather_sym = 1;              // pull gather: 1 = sum the upper triangle only and store each block into its mirror slot too, 0 = every slot sums its own list
   int gather_mode = 1;             // 1 = lane per slot (gather_blocks_kernel, default), 9 = nine lanes per block (gather_blocks9_kernel: 41 % fewer L1 sectors, same time -- DESIGN 4)
@@ -1036,8 +1036,10 @@ static int element_pass(fea_gpu_ctx *c, bool with_k, bool with_r, bool chunk_bc 
     phase_begin(c, PH_ELEM);
     // The ~2 x chunks launches and their cross-stream dependencies are captured once per variant into a CUDA
     // graph: issued one by one from the host they cost more than the kernels take.
-    const int key = (with_r ? 1 : 0) | (chunk_bc ? 2 : 0) | ((c->cells_dbg & 7) << 2) | (push ? 32 : 0) | (c->chunk_overlap ? 64 : 0) |
-                    ((c->gather_split & 15) << 7) | (c->chunk_tiles << 11);
+    // everything a captured launch sequence depends on besides the (fixed) device pointers and material constants
+    const int64_t key = (with_r ? 1 : 0) | (chunk_bc ? 2 : 0) | ((c->cells_dbg & 7) << 2) | (push ? 32 : 0) | (c->chunk_overlap ? 64 : 0) |
+                        ((c->gather_split & 15) << 7) | (c->elem_ratio ? 1 << 11 : 0) | ((int64_t)(c->gather_threads >> 7) << 12) |
+                        ((int64_t)c->chunk_tiles << 16);
     auto it = c->asm_graphs.find(key);
     if (it == c->asm_graphs.end()) {
       const int n_chunks = (int)c->chunk_cols.size() - 1;
