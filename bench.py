@@ -356,7 +356,7 @@ def window_parity(g, args, world, rank, n_nodes_full):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 60: ~0.2 s of device time, enough clock samples; 20 for --impl reference, whose steps are seconds of CPU work)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--n", type=int, default=55, help="cubes per edge per GPU (55 -> 998 250 tets)")
@@ -375,6 +375,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 60
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3
 
